@@ -1,0 +1,143 @@
+"""ctypes binding to ``lib/librocnrdma_b200.so`` (the flat ``rn_*`` C ABI).
+
+The library is built in-tree by :mod:`rocnrdma_b200.build`.  If it is missing and
+nvcc is available it is built on first use; on a GPU box a missing library is a
+hard error -- there is no Python fallback for the data path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_LIB = None
+_LIB_PATH = Path(__file__).resolve().parent / "lib" / "librocnrdma_b200.so"
+
+u8, u16, u32, u64, i32 = C.c_uint8, C.c_uint16, C.c_uint32, C.c_uint64, C.c_int
+vp = C.c_void_p
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class RnWc(C.Structure):
+    _fields_ = [("qpn", u32), ("byte_cnt", u32), ("imm", u32), ("wqe_counter", u16),
+                ("opcode", u8), ("syndrome", u8), ("wqe_opcode", u8), ("is_error", u8)]
+
+
+class RnRemote(C.Structure):
+    _fields_ = [("rkeys", u64), ("n_rkeys", u32), ("qpn", u32), ("rq", u64), ("rq_dbr", u64),
+                ("rq_log", u32), ("pad", u32), ("rcq", u64), ("rcq_buf", u64)]
+
+
+class RnQpCounters(C.Structure):
+    _fields_ = [("n_wqe", u64), ("n_cqe", u64), ("n_err", u64), ("n_db_order_violations", u64),
+                ("n_bytes", u64), ("n_rnr", u64), ("resv_head", u64), ("ready_head", u64),
+                ("sq_cons", u64), ("cursor", u64), ("retire_head", u64), ("state", u32), ("pad", u32)]
+
+
+class RnEngineStats(C.Structure):
+    _fields_ = [("n_polls", u64), ("n_chunks", u64), ("n_bulk_chunks", u64), ("dbg_last_db", u64),
+                ("dbg_t_start", u64), ("dbg_t_exit", u64), ("dbg_last_state", u64), ("running_ctas", u32),
+                ("exited_idle", u32), ("n_qps", u32), ("ctas", u32)]
+
+
+_SIGS = {
+    "rn_last_error": (C.c_char_p, []),
+    "rn_abi_sizes": (i32, [C.POINTER(u32), i32]),
+    "rn_hca_open": (i32, [i32, u32, u32, u64, u64, C.POINTER(vp)]),
+    "rn_hca_close": (i32, [vp]),
+    "rn_hca_mkey_table": (u64, [vp]),
+    "rn_hca_arena": (u64, [vp, C.POINTER(u64)]),
+    "rn_classify_ptr": (i32, [u64, C.POINTER(i32)]),
+    "rn_reg_mr": (i32, [vp, u64, u64, u32, C.POINTER(u32)]),
+    "rn_mr_revoke": (i32, [vp, u32]),
+    "rn_dereg_mr": (i32, [vp, u32]),
+    "rn_mr_state": (i32, [vp, u32]),
+    "rn_create_cq": (i32, [vp, u32, u32, C.POINTER(vp)]),
+    "rn_cq_dev": (u64, [vp]),
+    "rn_poll_cq": (i32, [vp, i32, C.POINTER(RnWc)]),
+    "rn_create_qp": (i32, [vp, vp, vp, u32, u32, u32, u32, C.POINTER(vp)]),
+    "rn_qp_dev": (u64, [vp]),
+    "rn_qp_num": (u32, [vp]),
+    "rn_qp_state": (u32, [vp]),
+    "rn_qp_describe": (i32, [vp, C.POINTER(RnRemote)]),
+    "rn_qp_connect": (i32, [vp, C.POINTER(RnRemote)]),
+    "rn_modify_qp": (i32, [vp, u32]),
+    "rn_qp_connect_pair": (i32, [vp, vp]),
+    "rn_qp_query": (i32, [vp, C.POINTER(RnQpCounters)]),
+    "rn_post_send": (i32, [vp, u32, u64, u32, u64, u32, u32, u32, u32, C.POINTER(u64)]),
+    "rn_post_recv": (i32, [vp, u64, u32, u32]),
+    "rn_engine_running": (i32, [vp]),
+    "rn_engine_start": (i32, [vp, i32, u64, u64]),
+    "rn_engine_stop": (i32, [vp]),
+    "rn_engine_stats": (i32, [vp, C.POINTER(RnEngineStats)]),
+    "rn_hca_scratch": (u64, [vp, C.POINTER(u64)]),
+    "rn_hca_work_stream": (u64, [vp]),
+    "rn_k_rdma_stream": (i32, [u64, C.POINTER(u64), u32, u32, u64, u32, u64, u32, u64, u32, u32, u32, u32, u64, u32, u64, u64]),
+    "rn_wire_build_wqe": (None, [C.POINTER(u8), u32, u32, u32, u64, u32, u64, u32, u32, u32, u32]),
+    "rn_wire_decode_cqe": (i32, [C.POINTER(u8), C.POINTER(RnWc)]),
+    "rn_k_fill_random": (i32, [u64, u64, u64, u64]),
+    "rn_k_fill_bf16": (i32, [u64, u64, u64, u64, C.c_float]),
+    "rn_k_checksum": (i32, [u64, u64, u64, u64]),
+    "rn_k_compare": (i32, [u64, u64, u64, u64, u64]),
+    "rn_k_l2_flush": (i32, [u64, u64, u64, u32]),
+}
+
+# Symbols that later build stages add; bound when present so partial builds import.
+_OPTIONAL_SIGS: dict = {}
+
+
+def register_optional(name, restype, argtypes):
+    _OPTIONAL_SIGS[name] = (restype, argtypes)
+    if _LIB is not None:
+        _bind(_LIB, name, restype, argtypes, optional=True)
+
+
+def _bind(lib, name, restype, argtypes, optional=False):
+    try:
+        fn = getattr(lib, name)
+    except AttributeError:
+        if optional:
+            return
+        raise NativeError(f"{_LIB_PATH} lacks symbol {name}; rebuild with `python -m rocnrdma_b200.build --force`")
+    fn.restype = restype
+    fn.argtypes = argtypes
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def available() -> bool:
+    return _LIB_PATH.exists()
+
+
+def load():
+    """Load (building if needed) the native library and return the ctypes handle."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not _LIB_PATH.exists():
+        if os.environ.get("ROCNRDMA_NO_AUTOBUILD"):
+            raise NativeError(f"{_LIB_PATH} not built; run `python -m rocnrdma_b200.build`")
+        from . import build as _build
+        _build.build()
+    # Belt and braces with rn_hca_open's explicit preload: no lazy code loading, which
+    # would stall behind the resident engine kernel.
+    os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+    lib = C.CDLL(str(_LIB_PATH), mode=C.RTLD_GLOBAL)
+    for name, (res, args) in _SIGS.items():
+        _bind(lib, name, res, args)
+    for name, (res, args) in _OPTIONAL_SIGS.items():
+        _bind(lib, name, res, args, optional=True)
+    _LIB = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().rn_last_error().decode(errors="replace")
+        raise NativeError(f"{what or 'native call'} failed (rc={rc}): {msg}")
+    return rc

@@ -1,0 +1,291 @@
+"""Verbs-shaped public API over the native software HCA.
+
+    ctx = Context(device=0)                      # ~ ibv_open_device + alloc_pd
+    mr  = ctx.reg_mr(tensor)                     # ~ ibv_reg_mr on a GPU pointer (the reference's whole purpose)
+    cq  = ctx.create_cq(1024)
+    qp  = ctx.create_qp(cq)                      # RC queue pair
+    qp.connect(peer_qp)                          # RESET->INIT->RTR->RTS both ways
+    ctx.engine_start(ctas=32)                    # the DMA engine (the "NIC")
+    qp.post_write(src_mr, dst_mr, nbytes)        # host-posted   (baseline: SURVEY.md B2)
+    ops.rdma_stream(qp, ...)                     # GPU-posted    (product:  SURVEY.md P1)
+
+Reference parity: ``reg_mr`` is what amdp2p's seven peer-memory callbacks make
+possible (amdp2p.c:363-371); revocation (``MemoryRegion.revoke``) is
+free_callback (amdp2p.c:88-109).  Everything below registration has no
+counterpart there.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional
+
+from . import _native as N
+from . import wire as W
+
+
+def _ptr_len(buf, nbytes=None):
+    """Accept a torch tensor, a (ptr, nbytes) tuple, or an object with __cuda_array_interface__."""
+    if isinstance(buf, tuple):
+        return int(buf[0]), int(buf[1])
+    if hasattr(buf, "data_ptr"):
+        n = buf.numel() * buf.element_size()
+        return int(buf.data_ptr()), int(n if nbytes is None else nbytes)
+    if hasattr(buf, "ctypes"):  # numpy
+        return int(buf.ctypes.data), int(buf.nbytes if nbytes is None else nbytes)
+    raise TypeError(f"cannot take the address of {type(buf)!r}")
+
+
+@dataclass
+class WorkCompletion:
+    qpn: int
+    wqe_counter: int
+    opcode: int
+    byte_cnt: int
+    imm: int
+    syndrome: int
+    wqe_opcode: int
+    is_error: bool
+
+    @property
+    def status(self) -> str:
+        return W.SYNDROMES.get(self.syndrome, hex(self.syndrome))
+
+
+class MemoryRegion:
+    def __init__(self, ctx: "Context", addr: int, length: int, key: int, access: int, keepalive=None):
+        self.ctx, self.addr, self.length, self.key, self.access = ctx, addr, length, key, access
+        self.lkey = self.rkey = key
+        self._keepalive = keepalive
+        self._live = True
+
+    @property
+    def state(self) -> str:
+        return ["FREE", "PINNED", "REVOKED"][self.ctx._lib.rn_mr_state(self.ctx._h, self.key)]
+
+    def revoke(self):
+        """The backing memory is going away: stop translating now (the engine fails
+        any WQE that names this key with a protection error)."""
+        N.check(self.ctx._lib.rn_mr_revoke(self.ctx._h, self.key), "mr_revoke")
+
+    def dereg(self):
+        if self._live:
+            N.check(self.ctx._lib.rn_dereg_mr(self.ctx._h, self.key), "dereg_mr")
+            self._live = False
+            self._keepalive = None
+
+    def __repr__(self):
+        return f"MemoryRegion(addr=0x{self.addr:x}, len={self.length}, key=0x{self.key:x})"
+
+
+class CompletionQueue:
+    def __init__(self, ctx, handle, depth, mem):
+        self.ctx, self._c, self.depth, self.mem = ctx, handle, depth, mem
+
+    @property
+    def dev_ptr(self) -> int:
+        return self.ctx._lib.rn_cq_dev(self._c)
+
+    def poll(self, max_entries: int = 16) -> List[WorkCompletion]:
+        arr = (N.RnWc * max_entries)()
+        n = self.ctx._lib.rn_poll_cq(self._c, max_entries, arr)
+        if n < 0:
+            raise N.NativeError(f"poll_cq failed ({n})")
+        return [WorkCompletion(a.qpn, a.wqe_counter, a.opcode, a.byte_cnt, a.imm, a.syndrome, a.wqe_opcode,
+                               bool(a.is_error)) for a in arr[:n]]
+
+    def wait(self, n: int = 1, timeout_s: float = 5.0) -> List[WorkCompletion]:
+        import time
+        out: List[WorkCompletion] = []
+        t0 = time.monotonic()
+        while len(out) < n:
+            out += self.poll(n - len(out))
+            if len(out) < n and time.monotonic() - t0 > timeout_s:
+                raise TimeoutError(f"CQ wait: got {len(out)}/{n} completions in {timeout_s}s")
+        return out
+
+
+class QueuePair:
+    def __init__(self, ctx, handle, scq, rcq, sq_depth, rq_depth, sq_mem):
+        self.ctx, self._q, self.scq, self.rcq = ctx, handle, scq, rcq
+        self.sq_depth, self.rq_depth, self.sq_mem = sq_depth, rq_depth, sq_mem
+        self.qpn = ctx._lib.rn_qp_num(handle)
+
+    @property
+    def dev_ptr(self) -> int:
+        return self.ctx._lib.rn_qp_dev(self._q)
+
+    @property
+    def state(self) -> str:
+        return W.QP_STATE_NAMES[self.ctx._lib.rn_qp_state(self._q)]
+
+    def modify(self, state: int):
+        N.check(self.ctx._lib.rn_modify_qp(self._q, state), "modify_qp")
+
+    def describe(self) -> N.RnRemote:
+        r = N.RnRemote()
+        N.check(self.ctx._lib.rn_qp_describe(self._q, C.byref(r)), "qp_describe")
+        return r
+
+    def connect_remote(self, remote: N.RnRemote):
+        N.check(self.ctx._lib.rn_qp_connect(self._q, C.byref(remote)), "qp_connect")
+
+    def connect(self, peer: Optional["QueuePair"] = None):
+        """Bring this QP and ``peer`` (default: itself, i.e. loopback) to RTS."""
+        peer = peer or self
+        N.check(self.ctx._lib.rn_qp_connect_pair(self._q, peer._q), "qp_connect_pair")
+        return self
+
+    # ---- host-posted verbs (the "ibv_post_send" baseline path)
+    def _post(self, opcode, laddr, lkey, raddr, rkey, nbytes, signaled=True, imm=0) -> int:
+        idx = C.c_uint64()
+        flags = W.CTRL_CQ_UPDATE if signaled else 0
+        N.check(self.ctx._lib.rn_post_send(self._q, opcode, laddr, lkey, raddr, rkey, nbytes, flags, imm,
+                                           C.byref(idx)), "post_send")
+        return idx.value
+
+    def post_write(self, src: MemoryRegion, dst: MemoryRegion, nbytes=None, src_off=0, dst_off=0, signaled=True,
+                   imm=None) -> int:
+        n = src.length - src_off if nbytes is None else nbytes
+        op = W.OP_RDMA_WRITE if imm is None else W.OP_RDMA_WRITE_IMM
+        return self._post(op, src.addr + src_off, src.lkey, dst.addr + dst_off, dst.rkey, n, signaled, imm or 0)
+
+    def post_read(self, dst_local: MemoryRegion, src_remote: MemoryRegion, nbytes=None, local_off=0, remote_off=0,
+                  signaled=True) -> int:
+        n = dst_local.length - local_off if nbytes is None else nbytes
+        return self._post(W.OP_RDMA_READ, dst_local.addr + local_off, dst_local.lkey, src_remote.addr + remote_off,
+                          src_remote.rkey, n, signaled)
+
+    def post_send(self, src: MemoryRegion, nbytes=None, src_off=0, signaled=True, imm=None) -> int:
+        n = src.length - src_off if nbytes is None else nbytes
+        op = W.OP_SEND if imm is None else W.OP_SEND_IMM
+        return self._post(op, src.addr + src_off, src.lkey, 0, 0, n, signaled, imm or 0)
+
+    def post_raw(self, opcode, laddr=0, lkey=0, raddr=0, rkey=0, nbytes=0, signaled=True, imm=0) -> int:
+        return self._post(opcode, laddr, lkey, raddr, rkey, nbytes, signaled, imm)
+
+    def post_recv(self, dst: MemoryRegion, nbytes=None, off=0):
+        n = dst.length - off if nbytes is None else nbytes
+        N.check(self.ctx._lib.rn_post_recv(self._q, dst.addr + off, dst.lkey, n), "post_recv")
+
+    def counters(self) -> dict:
+        c = N.RnQpCounters()
+        N.check(self.ctx._lib.rn_qp_query(self._q, C.byref(c)), "qp_query")
+        d = {k: getattr(c, k) for k, _ in c._fields_ if k != "pad"}
+        d["state"] = W.QP_STATE_NAMES[d["state"]]
+        return d
+
+
+class Context:
+    """One software HCA bound to one GPU (one per process in multi-GPU runs)."""
+
+    def __init__(self, device: int = 0, max_mkeys: int = 1024, max_qps: int = 256, arena_bytes: int = 64 << 20,
+                 host_arena_bytes: int = 16 << 20):
+        self._lib = N.load()
+        h = C.c_void_p()
+        N.check(self._lib.rn_hca_open(device, max_mkeys, max_qps, arena_bytes, host_arena_bytes, C.byref(h)), "hca_open")
+        self._h = h
+        self.device = device
+        self._mrs: List[MemoryRegion] = []
+        self._closed = False
+        self._stream = None
+        sz = C.c_uint64()
+        self._scratch_ptr = self._lib.rn_hca_scratch(self._h, C.byref(sz))
+        self._scratch_size = sz.value
+
+    def scratch(self, nbytes: int, offset: int = 0):
+        """(address, ctypes view) of the HCA's mapped pinned result area.  Kernels write
+        their status/timing words here and the host reads them after a stream sync, so the
+        hot path performs no CUDA allocation or memcpy (either would stall behind the
+        running engine kernel)."""
+        if offset + nbytes > self._scratch_size:
+            raise ValueError("scratch request too large")
+        addr = self._scratch_ptr + offset
+        return addr, (C.c_uint8 * nbytes).from_address(addr)
+
+    @property
+    def stream(self):
+        """The context's non-blocking work stream (a ``torch.cuda.Stream``).
+
+        Kernels that post to, or wait on, the engine MUST run on a non-blocking stream:
+        a kernel launched on the legacy default stream is serialised behind the
+        persistent engine kernel by the driver (measured on B200, driver 580: the poster
+        started 95 us after the engine's watchdog exit).  ``ops.*`` default to this
+        stream; wrap torch work that must overlap the engine in
+        ``with torch.cuda.stream(ctx.stream):``.
+        """
+        if self._stream is None:
+            import torch
+            # Created natively in rn_hca_open (before any engine runs): creating a stream
+            # while the engine kernel is resident stalls until the engine exits.
+            self._stream = torch.cuda.ExternalStream(self._lib.rn_hca_work_stream(self._h), device=self.device)
+        return self._stream
+
+    # ---- registration
+    def classify(self, buf) -> str:
+        ptr, _ = _ptr_len(buf, 1)
+        dev = C.c_int(-1)
+        return ["host", "device", "pinned_host", "managed"][self._lib.rn_classify_ptr(ptr, C.byref(dev))]
+
+    def reg_mr(self, buf, nbytes=None, access: int = W.ACC_ALL, offset: int = 0) -> MemoryRegion:
+        ptr, n = _ptr_len(buf, nbytes)
+        key = C.c_uint32()
+        N.check(self._lib.rn_reg_mr(self._h, ptr + offset, n, access, C.byref(key)), "reg_mr")
+        mr = MemoryRegion(self, ptr + offset, n, key.value, access, keepalive=buf)
+        self._mrs.append(mr)
+        return mr
+
+    # ---- queues
+    def create_cq(self, depth: int = 1024, mem: int = W.MEM_DEVICE) -> CompletionQueue:
+        c = C.c_void_p()
+        N.check(self._lib.rn_create_cq(self._h, depth, mem, C.byref(c)), "create_cq")
+        return CompletionQueue(self, c, depth, mem)
+
+    def create_qp(self, scq: CompletionQueue, rcq: Optional[CompletionQueue] = None, sq_depth: int = 256,
+                  rq_depth: int = 256, sq_mem: int = W.MEM_DEVICE, chunk_bytes: int = 128 << 10) -> QueuePair:
+        q = C.c_void_p()
+        rcq = rcq or scq
+        N.check(self._lib.rn_create_qp(self._h, scq._c, rcq._c, sq_depth, rq_depth, sq_mem, chunk_bytes, C.byref(q)),
+                "create_qp")
+        return QueuePair(self, q, scq, rcq, sq_depth, rq_depth, sq_mem)
+
+    def loopback_qp(self, depth: int = 256, mem: int = W.MEM_DEVICE, chunk_bytes: int = 128 << 10,
+                    cq_depth: Optional[int] = None) -> QueuePair:
+        cq = self.create_cq(cq_depth or max(2 * depth, 64), mem)
+        return self.create_qp(cq, cq, depth, depth, mem, chunk_bytes).connect()
+
+    # ---- engine
+    def engine_start(self, ctas: int = 32, idle_timeout_ms: int = 5000, rnr_timeout_ms: int = 500):
+        N.check(self._lib.rn_engine_start(self._h, ctas, idle_timeout_ms, rnr_timeout_ms), "engine_start")
+
+    def engine_stop(self):
+        N.check(self._lib.rn_engine_stop(self._h), "engine_stop")
+
+    @property
+    def engine_running(self) -> bool:
+        return bool(self._lib.rn_engine_running(self._h))
+
+    def engine_stats(self) -> dict:
+        s = N.RnEngineStats()
+        N.check(self._lib.rn_engine_stats(self._h, C.byref(s)), "engine_stats")
+        return {k: getattr(s, k) for k, _ in s._fields_}
+
+    def mkey_table_ptr(self) -> int:
+        return self._lib.rn_hca_mkey_table(self._h)
+
+    def close(self):
+        if not self._closed:
+            self._closed = True
+            self._lib.rn_hca_close(self._h)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,120 @@
+"""In-tree native build: nvcc -> rocnrdma_b200/lib/librocnrdma_b200.so (sm_100a only).
+
+The shared object exports a flat C ABI (``rn_*``) that ``rocnrdma_b200._native``
+loads with ctypes; keeping torch's C++ headers out of the build keeps a full
+rebuild to well under a minute and the .so free of ABI coupling to the torch
+wheel.  Replaces the reference's kbuild Makefiles for the userspace half
+(Makefile:1-71, tests/Makefile:1-69); the kernel modules keep real kbuild
+Makefiles under ``kmod/``.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+CSRC = ROOT / "csrc"
+LIBDIR = ROOT / "lib"
+LIB = LIBDIR / "librocnrdma_b200.so"
+
+CUDA_SOURCES = [
+    "hca/hca_host.cu",
+    "kernels/rdma_ops.cu",
+    "kernels/pack_fp8.cu",
+    "kernels/gemm_send.cu",
+]
+CXX_SOURCES = [
+    "reg/registration.cc",
+    "reg/p2ptest_user.cc",
+    "verbs/verbs_dl.cc",
+    "probe/probe.cc",
+]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall,-Wno-unused-function",
+    "--expt-relaxed-constexpr",
+    "-Xptxas", "-v",
+]
+CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-Wall", "-Wno-unused-function"]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _cuda_home() -> Path:
+    return Path(_nvcc()).resolve().parent.parent
+
+
+def _stamp(paths) -> str:
+    h = hashlib.sha256()
+    for p in sorted(paths):
+        h.update(str(p).encode())
+        h.update(p.read_bytes())
+    h.update(" ".join(NVCC_FLAGS + CXX_FLAGS).encode())
+    return h.hexdigest()
+
+
+def sources():
+    cu = [CSRC / s for s in CUDA_SOURCES if (CSRC / s).exists()]
+    cc = [CSRC / s for s in CXX_SOURCES if (CSRC / s).exists()]
+    return cu, cc
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile every native source for sm_100a and link the shared object."""
+    cu, cc = sources()
+    headers = list(CSRC.rglob("*.h")) + list(CSRC.rglob("*.cuh"))
+    stamp = _stamp(cu + cc + headers)
+    stamp_file = LIBDIR / ".build_stamp"
+    if not force and LIB.exists() and stamp_file.exists() and stamp_file.read_text() == stamp:
+        return LIB
+    LIBDIR.mkdir(exist_ok=True)
+    objdir = LIBDIR / "obj"
+    objdir.mkdir(exist_ok=True)
+    nvcc = _nvcc()
+    cuda_inc = _cuda_home() / "include"
+    objs = []
+    procs = []
+    logs = {}
+    for src in cu:
+        obj = objdir / (src.stem + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, "-I", str(CSRC), "-c", str(src), "-o", str(obj)]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for src in cc:
+        obj = objdir / (src.stem + ".o")
+        cmd = ["g++", *CXX_FLAGS, "-I", str(CSRC), "-I", str(cuda_inc), "-c", str(src), "-o", str(obj)]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        logs[src.name] = out
+        if p.returncode != 0:
+            failed = True
+            sys.stderr.write(f"--- {src} FAILED\n{out}\n")
+        elif verbose:
+            sys.stderr.write(f"--- {src}\n{out}\n")
+    if failed:
+        raise RuntimeError("native build failed")
+    (LIBDIR / "ptxas_info.txt").write_text("\n".join(f"=== {k}\n{v}" for k, v in logs.items()))
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *map(str, objs),
+            "-Xcompiler", "-fPIC", "-ldl", "-lpthread"]
+    subprocess.run(link, check=True)
+    stamp_file.write_text(stamp)
+    return LIB
+
+
+if __name__ == "__main__":
+    p = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(p)

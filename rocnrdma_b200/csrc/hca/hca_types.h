@@ -1,0 +1,142 @@
+// Device-visible state of the software HCA ("softhca").
+//
+// The softhca keeps the exact contract a ConnectX exposes to an IBGDA-style
+// poster -- a send queue of 64-byte WQEBBs, a doorbell record, a doorbell
+// register, a completion queue of 64-byte CQEs with an owner bit, and an MKey
+// table that turns (key, VA, length) into something the DMA engine may touch --
+// but the "NIC" is a persistent CUDA kernel (hca/engine.cu) that moves the bytes
+// over HBM / NVLink with TMA bulk copies.  It exists because the GPU box exposes
+// no /dev/infiniband to the container (gpurun probe); the verbs
+// backend (verbs/verbs_dl.cc) drives a real mlx5 QP through the same poster code.
+//
+// Reference parity: amd_mem_context (amdp2p.c:73-85) is the per-registration
+// record there; MKeyEntry is its analogue here (VA, size, owner, pin handle).
+#pragma once
+#include <stdint.h>
+#include "../wire/mlx5_wire.h"
+
+namespace rn {
+
+enum MemKind : uint32_t { MEM_DEVICE = 0, MEM_HOST_PINNED = 1, MEM_PEER = 2 };
+
+enum Access : uint32_t {
+  ACC_LOCAL_WRITE = 1u << 0,
+  ACC_REMOTE_WRITE = 1u << 1,
+  ACC_REMOTE_READ = 1u << 2,
+  ACC_REMOTE_ATOMIC = 1u << 3,
+};
+
+enum QpState : uint32_t {
+  QPS_RESET = 0, QPS_INIT = 1, QPS_RTR = 2, QPS_RTS = 3, QPS_SQD = 4, QPS_SQE = 5, QPS_ERR = 6,
+};
+
+// One registered memory region.  `base` is the VA the application registered and
+// puts into WQEs; `map_base` is the address through which the engine's GPU reaches
+// the same bytes (identical for local HBM and pinned host memory under UVA, an
+// IPC/VMM mapping for a peer GPU's HBM).
+struct alignas(16) MKeyEntry {
+  uint64_t base;
+  uint64_t len;
+  uint64_t map_base;
+  uint32_t key;       // (index << 8) | 8-bit variant tag ; lkey == rkey, as on mlx5
+  uint32_t access;
+  uint32_t valid;     // 0 = free or revoked
+  uint32_t kind;      // MemKind
+  uint64_t pad;
+};
+static_assert(sizeof(MKeyEntry) == 48, "engine reads an MKey as three 16-byte loads");
+
+struct CqDev {
+  uint8_t* buf;              // 2^log_n CQEs of 64 bytes
+  uint32_t* dbrec;           // [0] = be32(ci & 0xffffff), written by the consumer
+  uint32_t log_n;
+  uint32_t cqn;
+  unsigned int pi;           // producer index, claimed by engines with atomicAdd (system scope)
+  unsigned int ci;           // device consumer index (device pollers)
+  unsigned int overruns;
+  unsigned int pad;
+};
+
+// Per-SQ-slot record written by the WQE prologue (address translation, checks)
+// and shared by every engine CTA that copies a chunk of that WQE.
+struct alignas(64) Resolved {
+  uint64_t src, dst;
+  uint32_t bytes, nchunks;
+  uint32_t imm;
+  uint8_t opcode, fm_ce_se, syndrome, rq_consumed;
+  unsigned int done;          // chunks finished (atomic)
+  uint32_t chunk;             // bytes per claim for this WQE (sized so ~4 claims per engine CTA)
+  uint64_t rq_idx;            // receive WQE consumed (SEND / WRITE_IMM)
+  unsigned long long state;   // (wqe_index << 2) | 1 resolved | 2 finished
+  uint64_t pad1;
+};
+static_assert(sizeof(Resolved) == 64, "Resolved is one cache-line pair slot");
+
+// What a requester's engine needs to know about the connected responder QP.  All
+// pointers are already translated into the engine GPU's address space.
+struct RemoteView {
+  MKeyEntry* rkeys;           // responder's MKey table
+  uint32_t n_rkeys;
+  uint32_t qpn;
+  uint8_t* rq;                // responder receive ring (16-byte RecvWqe strides)
+  uint32_t* rq_dbr;           // responder doorbell record ([DBR_RCV] = be32 count)
+  uint32_t rq_log;
+  uint32_t connected;
+  CqDev* rcq;                 // responder's receive CQ
+  uint8_t* rcq_buf;           // its ring, translated
+};
+
+struct QpDev {
+  // ---- static after creation
+  uint32_t qpn;
+  volatile uint32_t state;    // QpState
+  uint8_t* sq;                // 2^sq_log WQEBBs
+  uint32_t sq_log;
+  uint32_t rq_log;
+  uint32_t* dbr;              // doorbell record: [DBR_RCV], [DBR_SND], be32 16-bit counters
+  unsigned long long* bf;     // doorbell register: first 8 bytes of the last ctrl segment
+  uint8_t* rq;                // own receive ring
+  CqDev* scq;                 // send CQ
+  CqDev* rcq;                 // receive CQ
+  MKeyEntry* lkeys;
+  uint32_t n_lkeys;
+  uint32_t chunk_bytes;       // engine work granule for this QP
+  RemoteView r;
+  Resolved* resolved;         // one per SQ slot
+  // ---- device poster state
+  unsigned long long resv_head;    // next WQE index to hand out
+  unsigned long long ready_head;   // every index below this has rung its doorbell
+  unsigned long long sq_cons;      // every index below this is complete (from CQEs)
+  unsigned long long rq_pi;        // receive WQEs posted
+  // ---- engine state
+  unsigned long long cursor;       // (wqe_index << 24) | chunk ; chunk 0xffffff = prologue lock
+  unsigned long long retire_head;  // next WQE index to retire in order
+  unsigned int retire_lock;
+  unsigned int pad0;
+  unsigned long long rq_head;      // next receive WQE of the *peer* to consume
+  unsigned long long rnr_since;    // globaltimer of the first receiver-not-ready for cursor WQE
+  // ---- counters (readable from the host; SURVEY.md section 5 "metrics")
+  unsigned long long n_wqe, n_cqe, n_err, n_db_order_violations, n_bytes, n_rnr;
+};
+
+enum : unsigned long long { CURSOR_LOCK = 0xffffffull, CURSOR_CHUNK_BITS = 24 };
+
+struct EngineCtl {
+  volatile uint32_t* stop;         // mapped pinned host word: nonzero = exit
+  QpDev** qps;                     // device array of QP pointers
+  volatile uint32_t n_qps;
+  uint32_t max_qps;
+  unsigned long long idle_timeout_ns;   // exit when no doorbell moved for this long
+  unsigned long long rnr_timeout_ns;
+  unsigned int running_ctas;       // CTAs alive (atomic)
+  unsigned int exited_idle;        // set when the watchdog ended the engine
+  unsigned int fatal;              // a DMA never completed; engine bailed out
+  unsigned int pad;
+  unsigned long long n_polls, n_chunks, n_bulk_chunks;
+  unsigned long long dbg_last_db, dbg_t_start, dbg_t_exit, dbg_last_state;
+};
+
+// Status codes returned by device-side waits (never spin forever: SURVEY.md section 5).
+enum WaitStatus : int { WAIT_OK = 0, WAIT_TIMEOUT = -1, WAIT_CQE_ERROR = -2, WAIT_QP_ERROR = -3 };
+
+}  // namespace rn

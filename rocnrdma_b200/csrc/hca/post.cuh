@@ -1,0 +1,239 @@
+// GPU-initiated posting: reserve an SQ slot, write the 64-byte WQE, publish the
+// doorbell record, ring the doorbell, poll the completion queue -- all from an
+// sm_100a thread, no host in the loop (kernels K1/K2).
+//
+// Ordering contract (what a ConnectX requires, and what the softhca engine checks
+// and counts violations of in QpDev::n_db_order_violations):
+//     WQE bytes  --fence.sys-->  doorbell record  --fence.sys-->  doorbell register
+// Multi-poster scheme: resv_head hands out indices, ready_head serialises the
+// doorbell so the register never runs ahead of a WQE that is still being written
+// (three-counter scheme: resv_head / ready_head / sq_cons).
+//
+// The reference leaves posting to host ibv_post_send (README.md:67); this file is
+// the part of the new build that has no counterpart there.
+#pragma once
+#include <cuda_runtime.h>
+#include "hca_types.h"
+
+namespace rn {
+namespace dev {
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __forceinline__ void st_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_v4_volatile(const void* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_u64_volatile(const void* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_u64_acquire(const void* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_u64_release(void* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_u32_volatile(const void* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_u32_volatile(void* p, uint32_t v) {
+  asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+
+// -------------------------------------------------------------- slot reservation
+// Returns the 64-bit index of the first of `n` consecutive WQEs, or ~0ull if the
+// queue stayed full past `timeout_ns` (the CQ is polled while waiting so that a
+// poster that never calls wait() still makes progress).
+__device__ int cq_poll_once(QpDev* qp);
+
+__device__ __forceinline__ unsigned long long sq_reserve(QpDev* qp, uint32_t n,
+                                                         unsigned long long timeout_ns = 2000000000ull) {
+  unsigned long long idx = atomicAdd(&qp->resv_head, (unsigned long long)n);
+  const unsigned long long depth = 1ull << qp->sq_log;
+  if (idx + n - ld_u64_volatile(&qp->sq_cons) <= depth) return idx;
+  unsigned long long t0 = globaltimer_ns();
+  while (idx + n - ld_u64_volatile(&qp->sq_cons) > depth) {
+    cq_poll_once(qp);
+    if (globaltimer_ns() - t0 > timeout_ns) return ~0ull;
+  }
+  return idx;
+}
+
+// -------------------------------------------------------------- WQE writers
+// Four 16-byte stores = one WQEBB.  Fields are big-endian on the wire.
+__device__ __forceinline__ void write_rdma_wqe(QpDev* qp, unsigned long long idx, uint8_t opcode,
+                                               uint64_t laddr, uint32_t lkey, uint64_t raddr,
+                                               uint32_t rkey, uint32_t bytes, uint8_t fm_ce_se,
+                                               uint32_t imm = 0) {
+  uint8_t* slot = qp->sq + ((idx & ((1ull << qp->sq_log) - 1)) << 6);
+  // ctrl: opmod_idx_opcode | qpn_ds | sig,rsvd,fm_ce_se | imm
+  st_v4(slot + 0, ctrl_word0(opcode, (uint16_t)idx), ctrl_word1(qp->qpn, 3), (uint32_t)fm_ce_se << 24,
+        be32(imm));
+  // raddr: be64 raddr | be32 rkey | 0      (be64 in memory = be32(hi), be32(lo))
+  st_v4(slot + 16, be32((uint32_t)(raddr >> 32)), be32((uint32_t)raddr), be32(rkey), 0u);
+  // data: be32 byte_count | be32 lkey | be64 addr
+  st_v4(slot + 32, be32(bytes & 0x7fffffffu), be32(lkey), be32((uint32_t)(laddr >> 32)), be32((uint32_t)laddr));
+  st_v4(slot + 48, 0u, 0u, 0u, 0u);
+}
+__device__ __forceinline__ void write_send_wqe(QpDev* qp, unsigned long long idx, uint8_t opcode,
+                                               uint64_t laddr, uint32_t lkey, uint32_t bytes,
+                                               uint8_t fm_ce_se, uint32_t imm = 0) {
+  uint8_t* slot = qp->sq + ((idx & ((1ull << qp->sq_log) - 1)) << 6);
+  st_v4(slot + 0, ctrl_word0(opcode, (uint16_t)idx), ctrl_word1(qp->qpn, 2), (uint32_t)fm_ce_se << 24,
+        be32(imm));
+  st_v4(slot + 16, be32(bytes & 0x7fffffffu), be32(lkey), be32((uint32_t)(laddr >> 32)), be32((uint32_t)laddr));
+  st_v4(slot + 32, 0u, 0u, 0u, 0u);
+  st_v4(slot + 48, 0u, 0u, 0u, 0u);
+}
+
+// -------------------------------------------------------------- doorbell
+// Publish WQEs [idx, idx+n): in index order, update the doorbell record, then ring
+// the doorbell register with the first 8 bytes of the last WQE's ctrl segment.
+__device__ __forceinline__ int sq_submit(QpDev* qp, unsigned long long idx, uint32_t n,
+                                         unsigned long long timeout_ns = 2000000000ull) {
+  fence_sys();  // WQE bytes visible (to the NIC / engine) before anything that announces them
+  if (ld_u64_volatile(&qp->ready_head) != idx) {
+    unsigned long long t0 = globaltimer_ns();
+    while (ld_u64_volatile(&qp->ready_head) != idx) {
+      if (globaltimer_ns() - t0 > timeout_ns) return WAIT_TIMEOUT;
+    }
+  }
+  unsigned long long last = idx + n - 1;
+  st_u32_volatile(&qp->dbr[DBR_SND], be32((uint32_t)((last + 1) & 0xffff)));
+  fence_sys();  // doorbell record before doorbell register
+  unsigned long long db = (unsigned long long)ctrl_word0(OP_NOP, (uint16_t)last) |
+                          ((unsigned long long)ctrl_word1(qp->qpn, 0) << 32);
+  // The opcode byte in the doorbell copy is informational; the engine and a real
+  // BlueFlame register both key on wqe_index + qpn.
+  st_u64_release(qp->bf, db);
+  st_u64_release(&qp->ready_head, idx + n);
+  return WAIT_OK;
+}
+
+// -------------------------------------------------------------- completion queue
+// Consume at most one CQE of the QP's send CQ.  Returns 1 if one was consumed, 0 if
+// none was ready, <0 on an error CQE (which also moves the QP to ERR).
+__device__ __forceinline__ int cq_poll_once(QpDev* qp) {
+  CqDev* cq = qp->scq;
+  unsigned int ci = *(volatile unsigned int*)&cq->ci;
+  const uint8_t* cqe = cq->buf + ((size_t)(ci & ((1u << cq->log_n) - 1)) << 6);
+  uint4 tail = ld_v4_volatile(cqe + 48);  // timestamp_l | sop_drop_qpn | wqe_counter,sig,op_own
+  uint8_t op_own = (uint8_t)(tail.w >> 24);
+  if (!cqe_valid(op_own, ci, cq->log_n)) return 0;
+  __threadfence();  // acquire: payload and the rest of the CQE are visible past this point
+  uint16_t wqe_counter = be16((uint16_t)(tail.w & 0xffff));
+  int rc = 1;
+  uint8_t opc = cqe_opcode(op_own);
+  if (opc == CQE_REQ_ERR || opc == CQE_RESP_ERR) rc = WAIT_CQE_ERROR;
+  // Expand the 16-bit counter against the current consumer position.
+  unsigned long long cons = ld_u64_volatile(&qp->sq_cons);
+  unsigned long long done = cons + (unsigned long long)((uint16_t)(wqe_counter + 1 - (uint16_t)cons));
+  if (atomicCAS(&cq->ci, ci, ci + 1) == ci) {
+    atomicMax(&qp->sq_cons, done);
+    st_u32_volatile(&cq->dbrec[0], be32((ci + 1) & 0xffffff));
+  }
+  return rc;
+}
+
+// Wait until WQE `idx` (and, RC being in-order, everything before it) completed.
+__device__ __forceinline__ int sq_wait(QpDev* qp, unsigned long long idx,
+                                       unsigned long long timeout_ns = 2000000000ull) {
+  unsigned long long t0 = 0;
+  int err = WAIT_OK;
+  for (unsigned it = 0;; ++it) {
+    if (ld_u64_volatile(&qp->sq_cons) > idx) return err;
+    int rc = cq_poll_once(qp);
+    if (rc < 0) err = rc;
+    if (rc == 0) {
+      if (qp->state == QPS_ERR && ld_u64_volatile(&qp->sq_cons) <= idx && it > 64) {
+        // keep draining: flushed WQEs still produce error CQEs
+      }
+      if (t0 == 0) t0 = globaltimer_ns();
+      else if ((it & 15) == 0 && globaltimer_ns() - t0 > timeout_ns) return WAIT_TIMEOUT;
+    }
+  }
+}
+
+// -------------------------------------------------------------- one-call verbs
+__device__ __forceinline__ unsigned long long rdma_write(QpDev* qp, uint64_t laddr, uint32_t lkey,
+                                                         uint64_t raddr, uint32_t rkey, uint32_t bytes,
+                                                         bool signaled = true) {
+  unsigned long long idx = sq_reserve(qp, 1);
+  if (idx == ~0ull) return idx;
+  write_rdma_wqe(qp, idx, OP_RDMA_WRITE, laddr, lkey, raddr, rkey, bytes, signaled ? CTRL_CQ_UPDATE : 0);
+  if (sq_submit(qp, idx, 1) != WAIT_OK) return ~0ull;
+  return idx;
+}
+__device__ __forceinline__ unsigned long long rdma_read(QpDev* qp, uint64_t laddr, uint32_t lkey,
+                                                        uint64_t raddr, uint32_t rkey, uint32_t bytes,
+                                                        bool signaled = true) {
+  unsigned long long idx = sq_reserve(qp, 1);
+  if (idx == ~0ull) return idx;
+  write_rdma_wqe(qp, idx, OP_RDMA_READ, laddr, lkey, raddr, rkey, bytes, signaled ? CTRL_CQ_UPDATE : 0);
+  if (sq_submit(qp, idx, 1) != WAIT_OK) return ~0ull;
+  return idx;
+}
+__device__ __forceinline__ unsigned long long rdma_send(QpDev* qp, uint64_t laddr, uint32_t lkey,
+                                                        uint32_t bytes, bool signaled = true,
+                                                        uint32_t imm = 0, bool with_imm = false) {
+  unsigned long long idx = sq_reserve(qp, 1);
+  if (idx == ~0ull) return idx;
+  write_send_wqe(qp, idx, with_imm ? OP_SEND_IMM : OP_SEND, laddr, lkey, bytes,
+                 signaled ? CTRL_CQ_UPDATE : 0, imm);
+  if (sq_submit(qp, idx, 1) != WAIT_OK) return ~0ull;
+  return idx;
+}
+
+// Post one receive WQE on the QP's own RQ (single poster per RQ).
+__device__ __forceinline__ void post_recv(QpDev* qp, uint64_t addr, uint32_t lkey, uint32_t bytes) {
+  unsigned long long i = qp->rq_pi;
+  uint8_t* slot = qp->rq + ((i & ((1ull << qp->rq_log) - 1)) << 4);
+  st_v4(slot, be32(bytes & 0x7fffffffu), be32(lkey), be32((uint32_t)(addr >> 32)), be32((uint32_t)addr));
+  fence_sys();
+  qp->rq_pi = i + 1;
+  st_u32_volatile(&qp->dbr[DBR_RCV], be32((uint32_t)((i + 1) & 0xffff)));
+  fence_sys();
+}
+
+// Poll the receive CQ for one completion.  Returns bytes received (>=0) and the
+// immediate through *imm, WAIT_TIMEOUT, or WAIT_CQE_ERROR.
+__device__ __forceinline__ long long recv_wait(QpDev* qp, uint32_t* imm, unsigned long long timeout_ns) {
+  CqDev* cq = qp->rcq;
+  unsigned long long t0 = globaltimer_ns();
+  for (unsigned it = 0;; ++it) {
+    unsigned int ci = *(volatile unsigned int*)&cq->ci;
+    const uint8_t* cqe = cq->buf + ((size_t)(ci & ((1u << cq->log_n) - 1)) << 6);
+    uint4 tail = ld_v4_volatile(cqe + 48);
+    uint8_t op_own = (uint8_t)(tail.w >> 24);
+    if (cqe_valid(op_own, ci, cq->log_n)) {
+      __threadfence();
+      uint4 mid = ld_v4_volatile(cqe + 32);  // srqn | imm | rsvd | byte_cnt
+      uint8_t opc = cqe_opcode(op_own);
+      if (atomicCAS(&cq->ci, ci, ci + 1) != ci) continue;
+      st_u32_volatile(&cq->dbrec[0], be32((ci + 1) & 0xffffff));
+      if (opc == CQE_RESP_ERR || opc == CQE_REQ_ERR) return WAIT_CQE_ERROR;
+      if (imm) *imm = be32(mid.y);
+      return (long long)be32(mid.w);
+    }
+    if ((it & 15) == 15 && globaltimer_ns() - t0 > timeout_ns) return WAIT_TIMEOUT;
+  }
+}
+
+}  // namespace dev
+}  // namespace rn

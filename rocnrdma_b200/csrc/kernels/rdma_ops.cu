@@ -1,0 +1,210 @@
+// K1 / K2 / K6: GPU-initiated RDMA write / read / send driver
+// kernels, plus the verification + device-timing helpers.
+//
+//   rdma_stream_kernel  one CTA per QP; lane 0 posts `iters` work requests with a
+//                       bounded window, polls the CQ on the device, stamps
+//                       %globaltimer around the whole exchange.  This is the
+//                       "ib_write_bw / ib_read_bw, but the poster is an SM" loop.
+//   fill / checksum / compare   random payloads and byte-exact verification.
+//
+// No counterpart in the reference (it has no data path: SURVEY.md section 3.2).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../hca/post.cuh"
+
+using namespace rn;
+using namespace rn::dev;
+
+#define RN_API extern "C" __attribute__((visibility("default")))
+
+constexpr int kMaxStreamQps = 64;
+struct StreamArgs {
+  QpDev* qps[kMaxStreamQps];   // one per CTA, by value: no device allocation on the hot path
+  uint32_t opcode;         // OP_RDMA_WRITE / OP_RDMA_READ / OP_SEND
+  uint64_t laddr, raddr;   // base addresses (per-CTA stride added)
+  uint64_t stride;         // address stride between CTAs' buffers
+  uint32_t lkey, rkey;
+  uint32_t bytes;          // message size
+  uint32_t iters;
+  uint32_t window;         // max outstanding WQEs per QP
+  uint32_t signal_every;   // 1 = every WQE signaled
+  uint64_t slot_stride;    // each iteration i uses offset (i % nslots) * slot_stride
+  uint32_t nslots;
+  uint64_t timeout_ns;
+  unsigned long long* out; // per CTA: [status, t_start, t_end, done, first_idx, last_idx, 0, 0]
+};
+
+__global__ void __launch_bounds__(32, 1) rdma_stream_kernel(StreamArgs a) {
+  if (threadIdx.x != 0) return;
+  QpDev* qp = a.qps[blockIdx.x];
+  unsigned long long* out = a.out + (size_t)blockIdx.x * 8;
+  const uint64_t lbase = a.laddr + blockIdx.x * a.stride, rbase = a.raddr + blockIdx.x * a.stride;
+  int status = WAIT_OK;
+  unsigned long long first = ~0ull, last = 0, done = 0;
+  const unsigned long long t0 = globaltimer_ns();
+  for (uint32_t i = 0; i < a.iters; ++i) {
+    if (a.window && done >= a.window) {
+      int rc = sq_wait(qp, last + 1 - a.window, a.timeout_ns);
+      if (rc != WAIT_OK) { status = rc; }
+      if (rc == WAIT_TIMEOUT) break;
+    }
+    unsigned long long idx = sq_reserve(qp, 1, a.timeout_ns);
+    if (idx == ~0ull) { status = WAIT_TIMEOUT; break; }
+    if (first == ~0ull) first = idx;
+    const uint64_t off = (uint64_t)(i % a.nslots) * a.slot_stride;
+    const bool sig = (a.signal_every <= 1) || ((i + 1) % a.signal_every == 0) || (i + 1 == a.iters);
+    const uint8_t flags = sig ? CTRL_CQ_UPDATE : 0;
+    if (a.opcode == OP_SEND)
+      write_send_wqe(qp, idx, OP_SEND, lbase + off, a.lkey, a.bytes, flags);
+    else
+      write_rdma_wqe(qp, idx, (uint8_t)a.opcode, lbase + off, a.lkey, rbase + off, a.rkey, a.bytes, flags);
+    if (sq_submit(qp, idx, 1, a.timeout_ns) != WAIT_OK) { status = WAIT_TIMEOUT; break; }
+    last = idx;
+    ++done;
+  }
+  if (done) {
+    int rc = sq_wait(qp, last, a.timeout_ns);
+    if (rc != WAIT_OK) status = rc;
+  }
+  const unsigned long long t1 = globaltimer_ns();
+  out[0] = (unsigned long long)(long long)status;
+  out[1] = t0; out[2] = t1; out[3] = done; out[4] = first; out[5] = last;
+  out[6] = ld_u64_volatile(&qp->sq_cons);
+  out[7] = 0;
+}
+
+RN_API int rn_k_rdma_stream(uint64_t stream, const uint64_t* qps_host, uint32_t nqp, uint32_t opcode, uint64_t laddr,
+                            uint32_t lkey, uint64_t raddr, uint32_t rkey, uint64_t stride, uint32_t bytes,
+                            uint32_t iters, uint32_t window, uint32_t signal_every, uint64_t slot_stride,
+                            uint32_t nslots, uint64_t timeout_ms, uint64_t out_dev) {
+  StreamArgs a;
+  if (nqp == 0 || nqp > (uint32_t)kMaxStreamQps) return -22;
+  for (uint32_t i = 0; i < nqp; ++i) a.qps[i] = (QpDev*)qps_host[i];
+  a.opcode = opcode; a.laddr = laddr; a.raddr = raddr; a.stride = stride;
+  a.lkey = lkey; a.rkey = rkey; a.bytes = bytes; a.iters = iters; a.window = window;
+  a.signal_every = signal_every ? signal_every : 1; a.slot_stride = slot_stride; a.nslots = nslots ? nslots : 1;
+  a.timeout_ns = (timeout_ms ? timeout_ms : 2000) * 1000000ull;
+  a.out = (unsigned long long*)out_dev;
+  rdma_stream_kernel<<<nqp, 32, 0, (cudaStream_t)stream>>>(a);
+  return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- K6: verification
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9e3779b97f4a7c15ull;
+  x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+  x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+  return x ^ (x >> 31);
+}
+
+__global__ void fill_random_kernel(uint64_t* p, size_t n64, uint8_t* tail, uint32_t ntail, uint64_t seed) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  for (; i < n64; i += step) p[i] = splitmix64(seed + i);
+  if (blockIdx.x == 0 && threadIdx.x < ntail) tail[threadIdx.x] = (uint8_t)splitmix64(seed + n64 + threadIdx.x);
+}
+
+// bf16 payload with a controlled dynamic range (for the fp8 pack tests/bench)
+__global__ void fill_bf16_kernel(uint16_t* p, size_t n, uint64_t seed, float scale) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += step) {
+    uint64_t r = splitmix64(seed + i);
+    // roughly normal via sum of 4 uniforms, times a per-32-block scale spread
+    float u = ((r & 0xffff) + ((r >> 16) & 0xffff) + ((r >> 32) & 0xffff) + ((r >> 48) & 0xffff)) * (1.0f / 65536.0f) - 2.0f;
+    float blk = 1.0f + (float)(splitmix64(seed ^ (i >> 5)) & 7);
+    float v = u * scale * blk;
+    uint32_t b = __float_as_uint(v);
+    b += 0x7fffu + ((b >> 16) & 1u);
+    p[i] = (uint16_t)(b >> 16);
+  }
+}
+
+__global__ void checksum_kernel(const uint64_t* p, size_t n64, const uint8_t* tail, uint32_t ntail,
+                                unsigned long long* out) {
+  unsigned long long acc = 0;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  for (; i < n64; i += step) acc += splitmix64(p[i] ^ i);
+  if (blockIdx.x == 0 && threadIdx.x < ntail) acc += splitmix64((uint64_t)tail[threadIdx.x] ^ (n64 + threadIdx.x));
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
+__global__ void compare_kernel(const uint8_t* a, const uint8_t* b, size_t n, unsigned long long* out) {
+  unsigned long long bad = 0;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  if ((((uintptr_t)a | (uintptr_t)b) & 15) == 0) {
+    const uint4 *a4 = (const uint4*)a, *b4 = (const uint4*)b;
+    size_t n4 = n / 16;
+    for (size_t k = i; k < n4; k += step) {
+      uint4 x = a4[k], y = b4[k];
+      if (x.x != y.x || x.y != y.y || x.z != y.z || x.w != y.w) ++bad;
+    }
+    for (size_t k = n4 * 16 + i; k < n; k += step) bad += a[k] != b[k];
+  } else {
+    for (size_t k = i; k < n; k += step) bad += a[k] != b[k];
+  }
+  for (int o = 16; o; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(out, bad);
+}
+
+RN_API int rn_k_fill_random(uint64_t stream, uint64_t ptr, uint64_t bytes, uint64_t seed) {
+  size_t n64 = bytes / 8;
+  uint32_t ntail = (uint32_t)(bytes % 8);
+  int grid = (int)((n64 + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  if (grid < 1) grid = 1;
+  fill_random_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((uint64_t*)ptr, n64, (uint8_t*)ptr + n64 * 8, ntail, seed);
+  return (int)cudaGetLastError();
+}
+RN_API int rn_k_fill_bf16(uint64_t stream, uint64_t ptr, uint64_t n, uint64_t seed, float scale) {
+  int grid = (int)((n + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  if (grid < 1) grid = 1;
+  fill_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((uint16_t*)ptr, n, seed, scale);
+  return (int)cudaGetLastError();
+}
+RN_API int rn_k_checksum(uint64_t stream, uint64_t ptr, uint64_t bytes, uint64_t out_dev) {
+  size_t n64 = bytes / 8;
+  uint32_t ntail = (uint32_t)(bytes % 8);
+  int grid = (int)((n64 + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  if (grid < 1) grid = 1;
+  cudaMemsetAsync((void*)out_dev, 0, 8, (cudaStream_t)stream);
+  checksum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint64_t*)ptr, n64, (const uint8_t*)ptr + n64 * 8, ntail,
+                                                          (unsigned long long*)out_dev);
+  return (int)cudaGetLastError();
+}
+RN_API int rn_k_compare(uint64_t stream, uint64_t a, uint64_t b, uint64_t bytes, uint64_t out_dev) {
+  int grid = (int)((bytes / 16 + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  if (grid < 1) grid = 1;
+  cudaMemsetAsync((void*)out_dev, 0, 8, (cudaStream_t)stream);
+  compare_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)a, (const uint8_t*)b, bytes,
+                                                         (unsigned long long*)out_dev);
+  return (int)cudaGetLastError();
+}
+
+// L2 flush between timed iterations: stream a buffer larger than the 126 MB L2.
+__global__ void l2_flush_kernel(uint4* p, size_t n4, uint32_t v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += step) p[i] = make_uint4(v, v, v, v);
+}
+RN_API int rn_k_l2_flush(uint64_t stream, uint64_t ptr, uint64_t bytes, uint32_t v) {
+  l2_flush_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>((uint4*)ptr, bytes / 16, v);
+  return (int)cudaGetLastError();
+}
+
+extern "C" __attribute__((visibility("default"))) void rn_preload_rdma_ops() {
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, rdma_stream_kernel);
+  cudaFuncGetAttributes(&a, fill_random_kernel);
+  cudaFuncGetAttributes(&a, fill_bf16_kernel);
+  cudaFuncGetAttributes(&a, checksum_kernel);
+  cudaFuncGetAttributes(&a, compare_kernel);
+  cudaFuncGetAttributes(&a, l2_flush_kernel);
+}

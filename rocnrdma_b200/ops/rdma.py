@@ -1,0 +1,116 @@
+"""K1 / K2 / K6 wrappers: GPU-initiated RDMA streams and verification helpers."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Sequence
+
+import torch
+
+from .. import _native as N
+from .. import wire as W
+
+WAIT_STATUS = {0: "OK", -1: "TIMEOUT", -2: "CQE_ERROR", -3: "QP_ERROR"}
+
+
+def _stream_ptr(stream=None) -> int:
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return int(s.cuda_stream)
+
+
+def work_stream(ctx, stream=None):
+    """Stream for engine-facing kernels: never the legacy default stream (see Context.stream)."""
+    if stream is not None and int(stream.cuda_stream) != 0:
+        return stream
+    cur = torch.cuda.current_stream(ctx.device)
+    return cur if int(cur.cuda_stream) != 0 else ctx.stream
+
+
+@dataclass
+class StreamResult:
+    status: List[str]
+    t_start_ns: List[int]
+    t_end_ns: List[int]
+    done: List[int]
+    bytes_per_msg: int
+
+    @property
+    def ok(self) -> bool:
+        return all(s == "OK" for s in self.status)
+
+    @property
+    def device_ns(self) -> int:
+        """Device-timed span: first QP start to last QP end (%globaltimer)."""
+        return max(self.t_end_ns) - min(self.t_start_ns)
+
+    @property
+    def gbps(self) -> float:
+        return sum(self.done) * self.bytes_per_msg / max(self.device_ns, 1)
+
+    @property
+    def us_per_msg(self) -> float:
+        return self.device_ns / 1e3 / max(max(self.done), 1)
+
+
+def rdma_stream(qps, opcode: int, src_mr, dst_mr, nbytes: int, iters: int = 1, window: int = 0,
+                signal_every: int = 1, stride: int = 0, slot_stride: int = 0, nslots: int = 1,
+                timeout_ms: int = 2000, stream=None, sync: bool = True, out=None):
+    """Launch the device poster: one CTA per QP posts ``iters`` work requests of
+    ``nbytes`` (window-limited), polls its CQ on the device and returns device times.
+
+    For RDMA_READ ``src_mr`` is the local destination and ``dst_mr`` the remote source,
+    mirroring the laddr/raddr roles in the WQE.
+    """
+    lib = N.load()
+    if not isinstance(qps, (list, tuple)):
+        qps = [qps]
+    ctx = qps[0].ctx
+    ws = work_stream(ctx, stream)
+    nq = len(qps)
+    qp_arr = (C.c_uint64 * nq)(*[q.dev_ptr for q in qps])
+    out_addr, out_view = ctx.scratch(nq * 64) if out is None else out
+    rc = lib.rn_k_rdma_stream(_stream_ptr(ws), qp_arr, nq, opcode, src_mr.addr, src_mr.lkey,
+                              dst_mr.addr if dst_mr is not None else 0, dst_mr.rkey if dst_mr is not None else 0,
+                              stride, nbytes, iters, window, signal_every, slot_stride, nslots, timeout_ms, out_addr)
+    if rc:
+        raise N.NativeError(f"rdma_stream launch failed: cuda error {rc}")
+    if not sync:
+        return out_view, ws
+    ws.synchronize()
+    return parse_stream_out(out_view, nq, nbytes)
+
+
+def parse_stream_out(out, nqp: int, nbytes: int) -> StreamResult:
+    words = (C.c_int64 * (nqp * 8)).from_buffer(out)
+    o = [list(words[i * 8:(i + 1) * 8]) for i in range(nqp)]
+    return StreamResult(status=[WAIT_STATUS.get(r[0], str(r[0])) for r in o], t_start_ns=[r[1] for r in o],
+                        t_end_ns=[r[2] for r in o], done=[r[3] for r in o], bytes_per_msg=nbytes)
+
+
+def fill_random(t: torch.Tensor, seed: int = 1, stream=None):
+    N.load().rn_k_fill_random(_stream_ptr(stream), t.data_ptr(), t.numel() * t.element_size(), seed)
+    return t
+
+
+def fill_bf16(t: torch.Tensor, seed: int = 1, scale: float = 1.0, stream=None):
+    assert t.dtype == torch.bfloat16
+    N.load().rn_k_fill_bf16(_stream_ptr(stream), t.data_ptr(), t.numel(), seed, scale)
+    return t
+
+
+def checksum(t: torch.Tensor, stream=None) -> int:
+    out = torch.zeros(1, dtype=torch.int64, device=t.device)
+    N.load().rn_k_checksum(_stream_ptr(stream), t.data_ptr(), t.numel() * t.element_size(), out.data_ptr())
+    return int(out.item()) & 0xFFFFFFFFFFFFFFFF
+
+
+def compare(a: torch.Tensor, b: torch.Tensor, nbytes=None, stream=None) -> int:
+    """Number of mismatching 16-byte words (aligned) or bytes (unaligned)."""
+    n = a.numel() * a.element_size() if nbytes is None else nbytes
+    out = torch.zeros(1, dtype=torch.int64, device=a.device)
+    N.load().rn_k_compare(_stream_ptr(stream), a.data_ptr(), b.data_ptr(), n, out.data_ptr())
+    return int(out.item())
+
+
+def l2_flush(scratch: torch.Tensor, value: int = 0, stream=None):
+    N.load().rn_k_l2_flush(_stream_ptr(stream), scratch.data_ptr(), scratch.numel() * scratch.element_size(), value)
