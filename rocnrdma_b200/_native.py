@@ -61,6 +61,8 @@ _SIGS = {
     "rn_create_qp": (i32, [vp, vp, vp, u32, u32, u32, u32, C.POINTER(vp)]),
     "rn_qp_dev": (u64, [vp]),
     "rn_qp_num": (u32, [vp]),
+    "rn_qp_set_flags": (i32, [vp, i32, i32]),
+    "rn_qp_read_trace": (i32, [vp, C.POINTER(u64), u32]),
     "rn_qp_state": (u32, [vp]),
     "rn_qp_describe": (i32, [vp, C.POINTER(RnRemote)]),
     "rn_qp_connect": (i32, [vp, C.POINTER(RnRemote)]),
@@ -124,9 +126,9 @@ def load():
             raise NativeError(f"{_LIB_PATH} not built; run `python -m rocnrdma_b200.build`")
         from . import build as _build
         _build.build()
-    # Belt and braces with rn_hca_open's explicit preload: no lazy code loading, which
-    # would stall behind the resident engine kernel.
-    os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+    # NOTE: do not set CUDA_MODULE_LOADING=EAGER here.  It would make the driver load every
+    # kernel of every library in the process (torch ships GBs of them) -- minutes on a cold
+    # box.  rn_hca_open preloads *our* kernels explicitly instead.
     lib = C.CDLL(str(_LIB_PATH), mode=C.RTLD_GLOBAL)
     for name, (res, args) in _SIGS.items():
         _bind(lib, name, res, args)

@@ -168,6 +168,19 @@ class QueuePair:
         n = dst.length - off if nbytes is None else nbytes
         N.check(self.ctx._lib.rn_post_recv(self._q, dst.addr + off, dst.lkey, n), "post_recv")
 
+    def set_flags(self, sys_scope: Optional[bool] = None, trace: Optional[bool] = None):
+        """sys_scope: force system-scope fences (peer GPU / NIC paths).  trace: stamp each
+        WQE's lifecycle (post, claim, parsed, copied, cqe, seen) with %globaltimer."""
+        N.check(self.ctx._lib.rn_qp_set_flags(self._q, -1 if sys_scope is None else int(sys_scope),
+                                              -1 if trace is None else int(trace)), "qp_set_flags")
+
+    def read_trace(self, nslots: Optional[int] = None) -> List[dict]:
+        n = nslots or self.sq_depth
+        buf = (C.c_uint64 * (n * 8))()
+        N.check(self.ctx._lib.rn_qp_read_trace(self._q, buf, n), "qp_read_trace")
+        names = ["post", "claim", "parsed", "copied", "cqe", "seen"]
+        return [{k: buf[i * 8 + j] for j, k in enumerate(names)} for i in range(n)]
+
     def counters(self) -> dict:
         c = N.RnQpCounters()
         N.check(self.ctx._lib.rn_qp_query(self._q, C.byref(c)), "qp_query")

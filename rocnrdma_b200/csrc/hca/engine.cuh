@@ -30,7 +30,7 @@ using namespace rn::dev;
 
 constexpr int kThreads = 128;
 constexpr uint32_t kSub = 16384;        // bytes per TMA bulk transaction
-constexpr int kStages = 6;              // smem ring depth (6 x 16 KiB = 96 KiB)
+constexpr int kStages = 12;             // smem ring depth (12 x 16 KiB = 192 KiB in flight per SM)
 constexpr uint32_t kBulkMin = 4096;     // below this the generic path is as fast
 
 // ------------------------------------------------------------------ PTX helpers
@@ -99,8 +99,8 @@ __device__ __forceinline__ uint64_t translate(const MKeyEntry* tab, uint32_t n, 
 // ------------------------------------------------------------------ CQE writer
 __device__ __forceinline__ void write_cqe(CqDev* cq, uint8_t* ring, uint8_t opcode, uint8_t wqe_opcode,
                                           uint32_t qpn, uint16_t wqe_counter, uint32_t byte_cnt, uint32_t imm,
-                                          uint8_t syndrome) {
-  unsigned int slot = atomicAdd_system(&cq->pi, 1u);
+                                          uint8_t syndrome, bool sys) {
+  unsigned int slot = sys ? atomicAdd_system(&cq->pi, 1u) : atomicAdd(&cq->pi, 1u);
   uint32_t log_n = cq->log_n;
   uint8_t* cqe = ring + ((size_t)(slot & ((1u << log_n) - 1)) << 6);
   uint8_t owner = (uint8_t)((slot >> log_n) & 1u);
@@ -118,7 +118,7 @@ __device__ __forceinline__ void write_cqe(CqDev* cq, uint8_t* ring, uint8_t opco
   uint32_t w52 = err ? ((uint32_t)syndrome << 24) : be32((uint32_t)now);
   uint32_t w56 = be32(((uint32_t)wqe_opcode << 24) | (qpn & 0xffffff));
   uint32_t w60 = (uint32_t)be16(wqe_counter) | ((uint32_t)cqe_op_own(opcode, owner) << 24);
-  fence_sys();  // payload + first 48 bytes before the word that flips ownership
+  fence_scope(sys);  // payload + first 48 bytes before the word that flips ownership
   st_v4(cqe + 48, w48, w52, w56, w60);
 }
 
@@ -245,7 +245,7 @@ __device__ __forceinline__ bool prologue(EngineCtl* ctl, QpDev* qp, unsigned lon
         if (now - qp->rnr_since < ctl->rnr_timeout_ns) return false;  // retry later
         syn = SYN_RNR_RETRY_EXC_ERR;
       } else {
-        __threadfence_system();
+        fence_scope(qp->sys_scope != 0);
         const uint8_t* rs = qp->r.rq + ((head & ((1ull << qp->r.rq_log) - 1)) << 4);
         uint4 d = ld_v4_volatile(rs);
         uint32_t rbytes = be32(d.x) & 0x7fffffffu, rlkey = be32(d.y);
@@ -267,7 +267,7 @@ __device__ __forceinline__ bool prologue(EngineCtl* ctl, QpDev* qp, unsigned lon
   // claim rate negligible while still load-balancing the tail.
   uint32_t chunk = qp->chunk_bytes;
   {
-    uint32_t target = 4u * gridDim.x;
+    uint32_t target = 8u * gridDim.x;
     uint32_t want = (uint32_t)(((uint64_t)v.bytes + target - 1) / target);
     want = (want + kSub - 1) / kSub * kSub;
     if (want > chunk) chunk = want;
@@ -281,19 +281,20 @@ __device__ __forceinline__ bool prologue(EngineCtl* ctl, QpDev* qp, unsigned lon
   r->opcode = v.opcode; r->fm_ce_se = v.fm_ce_se; r->syndrome = syn; r->rq_consumed = rq_taken;
   r->rq_idx = rq_idx;
   r->done = 0;
-  __threadfence();
   *(volatile unsigned long long*)&r->state = (w << 2) | 1ull;
   if (syn != SYN_OK && syn != SYN_WR_FLUSH_ERR) qp->state = QPS_ERR;
   atomicAdd(&qp->n_wqe, 1ull);
+  trace_stamp(qp, w, TR_PARSED);
   return true;
 }
 
 // ------------------------------------------------------------------ retire
 __device__ __forceinline__ void retire(QpDev* qp) {
   const uint32_t mask = (1u << qp->sq_log) - 1;
+  const bool sys = qp->sys_scope != 0;
   for (;;) {
     if (atomicCAS(&qp->retire_lock, 0u, 1u) != 0u) return;
-    __threadfence();
+    fence_gpu();  // acquire: retire_head and slot states written by the previous holder / finishers
     unsigned long long h = ld_u64_volatile(&qp->retire_head);
     for (;;) {
       Resolved* r = qp->resolved + (h & mask);
@@ -304,18 +305,19 @@ __device__ __forceinline__ void retire(QpDev* qp) {
         uint8_t ropc = err ? CQE_RESP_ERR
                            : (opc == OP_SEND ? CQE_RESP_SEND
                                              : (opc == OP_SEND_IMM ? CQE_RESP_SEND_IMM : CQE_RESP_WR_IMM));
-        write_cqe(qp->r.rcq, qp->r.rcq_buf, ropc, 0, qp->r.qpn, (uint16_t)r->rq_idx, r->bytes, r->imm, syn);
+        write_cqe(qp->r.rcq, qp->r.rcq_buf, ropc, 0, qp->r.qpn, (uint16_t)r->rq_idx, r->bytes, r->imm, syn, sys);
       }
       if (err || (r->fm_ce_se & CTRL_CQ_UPDATE)) {
-        write_cqe(qp->scq, qp->scq->buf, err ? CQE_REQ_ERR : CQE_REQ, opc, qp->qpn, (uint16_t)h, r->bytes, 0, syn);
-        atomicAdd(&qp->n_cqe, 1ull);
+        write_cqe(qp->scq, qp->scq->buf, err ? CQE_REQ_ERR : CQE_REQ, opc, qp->qpn, (uint16_t)h, r->bytes, 0, syn, sys);
+        trace_stamp(qp, h, TR_CQE);
+        qp->n_cqe = qp->n_cqe + 1;          // counters are only written under the retire lock
       }
-      if (err) atomicAdd(&qp->n_err, 1ull);
-      atomicAdd(&qp->n_bytes, (unsigned long long)r->bytes);
+      if (err) qp->n_err = qp->n_err + 1;
+      qp->n_bytes = qp->n_bytes + r->bytes;
       ++h;
     }
     *(volatile unsigned long long*)&qp->retire_head = h;
-    __threadfence();
+    fence_gpu();  // release
     atomicExch(&qp->retire_lock, 0u);
     Resolved* r = qp->resolved + (h & mask);
     if (ld_u64_volatile(&r->state) != ((h << 2) | 2ull)) return;
@@ -331,37 +333,63 @@ struct Work {
 
 __device__ __forceinline__ bool try_claim(EngineCtl* ctl, QpDev* qp, Work* out, bool* saw_pending) {
   if (qp->state != QPS_RTS && qp->state != QPS_ERR) return false;
-  unsigned long long cur = ld_u64_acquire(&qp->cursor);
+  const bool sys = qp->sys_scope != 0;
+  unsigned long long cur = ld_u64_volatile(&qp->cursor);
   unsigned long long w = cur >> CURSOR_CHUNK_BITS;
-  uint32_t c = (uint32_t)(cur & CURSOR_LOCK);
-  if (c == CURSOR_LOCK) { *saw_pending = true; return false; }
+  const uint32_t ph = (uint32_t)(cur & CURSOR_PHASE_MASK);
+  if (ph == PH_LOCKED) { *saw_pending = true; return false; }
   const uint32_t mask = (1u << qp->sq_log) - 1;
-  if (c == 0) {
+  if (ph == PH_UNPARSED) {
     unsigned long long db = ld_u64_volatile(qp->bf);
     uint32_t idx16 = (be32((uint32_t)db) >> 8) & 0xffff;
     uint32_t pending = (idx16 + 1 - (uint32_t)w) & 0xffff;
     if (pending == 0) return false;
     *saw_pending = true;
-    if (atomicCAS(&qp->cursor, cur, (w << CURSOR_CHUNK_BITS) | CURSOR_LOCK) != cur) return false;
-    __threadfence_system();
+    if (atomicCAS(&qp->cursor, cur, (w << CURSOR_CHUNK_BITS) | PH_LOCKED) != cur) return false;
+    fence_scope(sys);  // acquire: WQE bytes the doorbell announced
+    trace_stamp(qp, w, TR_CLAIM);
     // ordering audit: the doorbell record must already cover what the register announced
     uint32_t dbr16 = be32(ld_u32_volatile(&qp->dbr[DBR_SND])) & 0xffff;
     if (((dbr16 - (uint32_t)w) & 0xffff) < pending && ((dbr16 - (uint32_t)w) & 0xffff) < 0x8000)
       atomicAdd(&qp->n_db_order_violations, 1ull);
     if (!prologue(ctl, qp, w)) {
-      st_u64_release(&qp->cursor, w << CURSOR_CHUNK_BITS);  // receiver not ready: unlock, retry later
+      // receiver not ready: hand the WQE back (the one legal backwards move; nothing else
+      // can touch the cursor while it is PH_LOCKED)
+      atomicExch(&qp->cursor, w << CURSOR_CHUNK_BITS);
       return false;
     }
-    uint32_t n = qp->resolved[w & mask].nchunks;
-    st_u64_release(&qp->cursor, n > 1 ? ((w << CURSOR_CHUNK_BITS) | 1ull) : ((w + 1) << CURSOR_CHUNK_BITS));
+    Resolved* res = qp->resolved + (w & mask);
+    uint32_t n = res->nchunks;
+    if (n == 1) {
+      // Single-claim WQE: nobody else reads resolved[w] before retirement, so no ticket and
+      // no release fence -- just move the queue on (fire-and-forget RED, no round trip).
+      atomicMax(&qp->cursor, (w + 1) << CURSOR_CHUNK_BITS);
+      out->qp = qp; out->w = w; out->chunk = 0;
+      return true;
+    }
+    fence_gpu();  // release: resolved[] fields before the ticket that lets others read them
+    // Every cursor move from here on is an atomicMax, so it does not matter whether the
+    // ticket or the cursor becomes visible first: a draw on a not-yet-armed ticket sees the
+    // previous WQE's exhausted one, and a straggler that draws the last chunk early can only
+    // push the cursor forward.
+    st_u64_relaxed(&res->ticket, TICKET_ONE | ((w & TICKET_FIELD_MASK) << TICKET_GEN_SHIFT) | n);
+    atomicMax(&qp->cursor, (w << CURSOR_CHUNK_BITS) | PH_OFFER);
     out->qp = qp; out->w = w; out->chunk = 0;
     return true;
   }
+  // PH_OFFER: chunks of WQE w are on offer.  One fetch-add = one claim; the returned word
+  // carries (chunk, generation, nchunks), so a straggler that hits a recycled slot still
+  // holds a valid claim on whatever WQE the slot describes now.
   *saw_pending = true;
-  uint32_t n = *(volatile uint32_t*)&qp->resolved[w & mask].nchunks;
-  unsigned long long next = (c + 1 < n) ? ((w << CURSOR_CHUNK_BITS) | (c + 1)) : ((w + 1) << CURSOR_CHUNK_BITS);
-  if (atomicCAS(&qp->cursor, cur, next) != cur) return false;
-  out->qp = qp; out->w = w; out->chunk = c;
+  Resolved* res = qp->resolved + (w & mask);
+  unsigned long long t = atomicAdd(&res->ticket, (unsigned long long)TICKET_ONE);
+  uint32_t c = (uint32_t)(t >> 40), gen = (uint32_t)((t >> TICKET_GEN_SHIFT) & TICKET_FIELD_MASK);
+  uint32_t n = (uint32_t)(t & TICKET_FIELD_MASK);
+  if (c >= n) { __nanosleep(100); return false; }
+  unsigned long long wfull = w + ((gen - (uint32_t)w) & TICKET_FIELD_MASK);
+  if (c + 1 == n) atomicMax(&qp->cursor, (wfull + 1) << CURSOR_CHUNK_BITS);
+  fence_gpu();  // acquire: resolved[] fields of the generation this ticket names
+  out->qp = qp; out->w = wfull; out->chunk = c;
   return true;
 }
 
@@ -393,7 +421,7 @@ __global__ void __launch_bounds__(kThreads, 1) engine_kernel(EngineCtl* ctl) {
         if (n) { ctl->dbg_last_db = ld_u64_volatile(ctl->qps[0]->bf); ctl->dbg_last_state = ctl->qps[0]->state; }
       }
       for (uint32_t k = 0; k < n && !s.have_work; ++k) {
-        QpDev* qp = ctl->qps[(rr + k) % n];
+        QpDev* qp = *(QpDev* volatile*)&ctl->qps[(rr + k) % n];   // table grows while we run
         if (qp && try_claim(ctl, qp, &work, &pending)) {
           s.have_work = 1;
           rr = (rr + k) % n;
@@ -413,6 +441,7 @@ __global__ void __launch_bounds__(kThreads, 1) engine_kernel(EngineCtl* ctl) {
         ++spins;
         if (pending) last_activity = globaltimer_ns();
         if ((spins & 63) == 0) {
+          fence_gpu();  // drops stale L1 lines: host-side updates (new QPs, reconnects) become visible
           if (*ctl->stop) quit = 1;
           else if (globaltimer_ns() - last_activity > ctl->idle_timeout_ns) { quit = 1; ctl->exited_idle = 1; }
         }
@@ -442,11 +471,12 @@ __global__ void __launch_bounds__(kThreads, 1) engine_kernel(EngineCtl* ctl) {
     if (threadIdx.x == 0) {
       QpDev* qp = work.qp;
       Resolved* r = qp->resolved + (work.w & ((1u << qp->sq_log) - 1));
-      __threadfence_system();
-      unsigned int old = atomicAdd(&r->done, 1u);
-      if (old + 1 == r->nchunks) {
+      fence_scope(qp->sys_scope != 0);  // this chunk's bytes before the count that may complete the WQE
+      const uint32_t nch = r->nchunks;
+      if (nch == 1 || atomicAdd(&r->done, 1u) + 1 == nch) {
+        trace_stamp(qp, work.w, TR_COPIED);
+        fence_gpu();  // observe every other chunk's count -> their bytes precede our CQE
         *(volatile unsigned long long*)&r->state = (work.w << 2) | 2ull;
-        __threadfence();
         retire(qp);
       }
     }

@@ -434,8 +434,9 @@ RN_API int rn_create_qp(void* hca, void* scq, void* rcq, uint32_t nsq, uint32_t 
   uint32_t* dbr = (uint32_t*)arena_alloc(h, 64, host);
   unsigned long long* bf = (unsigned long long*)arena_alloc(h, 64, host);
   Resolved* res = (Resolved*)arena_alloc(h, (size_t)nsq * sizeof(Resolved), false);
+  unsigned long long* trace = (unsigned long long*)arena_alloc(h, (size_t)nsq * 64, false);
   q->d = (QpDev*)arena_alloc(h, sizeof(QpDev), false);
-  if (!sq || !rq || !dbr || !bf || !res || !q->d) { delete q; return fail(-12, "create_qp: control arena exhausted"); }
+  if (!sq || !rq || !dbr || !bf || !res || !trace || !q->d) { delete q; return fail(-12, "create_qp: control arena exhausted"); }
   memset(&q->h, 0, sizeof q->h);
   q->h.qpn = h->next_qpn++;
   q->h.state = QPS_RESET;
@@ -445,6 +446,9 @@ RN_API int rn_create_qp(void* hca, void* scq, void* rcq, uint32_t nsq, uint32_t 
   q->h.lkeys = h->d_mkeys; q->h.n_lkeys = h->max_mkeys;
   q->h.chunk_bytes = chunk_bytes;
   q->h.resolved = res;
+  q->h.trace = trace;
+  q->h.trace_on = 0;
+  q->h.sys_scope = (host || q->scq->mem == MEM_HOST_PINNED || q->rcq->mem == MEM_HOST_PINNED) ? 1 : 0;
   // doorbell register idle value: "last posted index = 0xffff" <=> nothing posted
   unsigned long long bf0 = (unsigned long long)ctrl_word0(OP_NOP, 0xffff) | ((unsigned long long)ctrl_word1(q->h.qpn, 0) << 32);
   int rc = 0;
@@ -456,6 +460,23 @@ RN_API int rn_create_qp(void* hca, void* scq, void* rcq, uint32_t nsq, uint32_t 
   return 0;
 }
 RN_API uint64_t rn_qp_dev(void* qp) { return (uint64_t)((Qp*)qp)->d; }
+// Force system-scope fences (peer-GPU or real-NIC connections) / toggle lifecycle tracing.
+RN_API int rn_qp_set_flags(void* qp, int sys_scope, int trace_on) {
+  Qp* q = (Qp*)qp;
+  cudaSetDevice(q->hca->dev);
+  int rc = 0;
+  if (sys_scope >= 0) { q->h.sys_scope = (uint32_t)sys_scope; rc = push(q->hca, &q->d->sys_scope, &q->h.sys_scope, 4); }
+  if (!rc && trace_on >= 0) { q->h.trace_on = (uint32_t)trace_on; rc = push(q->hca, &q->d->trace_on, &q->h.trace_on, 4); }
+  return rc;
+}
+// Copy out the lifecycle stamps of SQ slots [0, n): 8 u64 per slot.
+RN_API int rn_qp_read_trace(void* qp, uint64_t* out, uint32_t nslots) {
+  Qp* q = (Qp*)qp;
+  cudaSetDevice(q->hca->dev);
+  uint32_t depth = 1u << q->h.sq_log;
+  if (nslots > depth) nslots = depth;
+  return pull(q->hca, out, q->h.trace, (size_t)nslots * 64);
+}
 RN_API uint32_t rn_qp_num(void* qp) { return ((Qp*)qp)->h.qpn; }
 RN_API uint32_t rn_qp_state(void* qp) {
   Qp* q = (Qp*)qp;

@@ -68,7 +68,7 @@ struct alignas(64) Resolved {
   uint32_t chunk;             // bytes per claim for this WQE (sized so ~4 claims per engine CTA)
   uint64_t rq_idx;            // receive WQE consumed (SEND / WRITE_IMM)
   unsigned long long state;   // (wqe_index << 2) | 1 resolved | 2 finished
-  uint64_t pad1;
+  unsigned long long ticket;  // [63:40] next chunk | [39:20] wqe_index mod 2^20 | [19:0] nchunks
 };
 static_assert(sizeof(Resolved) == 64, "Resolved is one cache-line pair slot");
 
@@ -101,6 +101,9 @@ struct QpDev {
   MKeyEntry* lkeys;
   uint32_t n_lkeys;
   uint32_t chunk_bytes;       // engine work granule for this QP
+  uint32_t sys_scope;         // 1: some ring/peer of this QP is outside this GPU -> system-scope fences
+  uint32_t trace_on;          // 1: stamp the WQE lifecycle into trace[]
+  unsigned long long* trace;  // 8 x u64 per SQ slot: post, claim, parsed, copied, cqe, seen, -, -
   RemoteView r;
   Resolved* resolved;         // one per SQ slot
   // ---- device poster state
@@ -109,7 +112,7 @@ struct QpDev {
   unsigned long long sq_cons;      // every index below this is complete (from CQEs)
   unsigned long long rq_pi;        // receive WQEs posted
   // ---- engine state
-  unsigned long long cursor;       // (wqe_index << 24) | chunk ; chunk 0xffffff = prologue lock
+  unsigned long long cursor;       // (wqe_index << 24) | phase (PH_UNPARSED < PH_LOCKED < PH_OFFER)
   unsigned long long retire_head;  // next WQE index to retire in order
   unsigned int retire_lock;
   unsigned int pad0;
@@ -119,7 +122,12 @@ struct QpDev {
   unsigned long long n_wqe, n_cqe, n_err, n_db_order_violations, n_bytes, n_rnr;
 };
 
-enum : unsigned long long { CURSOR_LOCK = 0xffffffull, CURSOR_CHUNK_BITS = 24 };
+// cursor = (wqe_index << 24) | phase, phases ordered so that every legal move increases the
+// value and all updates can be atomicMax (a late store can never rewind the queue).
+enum : unsigned long long { CURSOR_CHUNK_BITS = 24, CURSOR_PHASE_MASK = 0xffffffull,
+                            PH_UNPARSED = 0, PH_LOCKED = 1, PH_OFFER = 2 };
+// Chunk tickets: one atomicAdd(TICKET_ONE) hands out a self-describing claim.
+enum : unsigned long long { TICKET_ONE = 1ull << 40, TICKET_GEN_SHIFT = 20, TICKET_FIELD_MASK = 0xfffffull };
 
 struct EngineCtl {
   volatile uint32_t* stop;         // mapped pinned host word: nonzero = exit

@@ -4,7 +4,8 @@
 //
 // Ordering contract (what a ConnectX requires, and what the softhca engine checks
 // and counts violations of in QpDev::n_db_order_violations):
-//     WQE bytes  --fence.sys-->  doorbell record  --fence.sys-->  doorbell register
+//     WQE bytes, doorbell record  --release (gpu scope on a device-local QP, sys otherwise)-->
+//     doorbell register
 // Multi-poster scheme: resv_head hands out indices, ready_head serialises the
 // doorbell so the register never runs ahead of a WQE that is still being written
 // (three-counter scheme: resv_head / ready_head / sq_cons).
@@ -55,6 +56,17 @@ __device__ __forceinline__ void st_u32_volatile(void* p, uint32_t v) {
   asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+__device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+// System scope only when something on the path lives outside this GPU (host-resident
+// rings, a peer GPU, a real NIC); a device-local QP pays the much cheaper gpu scope.
+__device__ __forceinline__ void fence_scope(bool sys) { if (sys) fence_sys(); else fence_gpu(); }
+__device__ __forceinline__ void st_u64_relaxed(void* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+enum TraceSlot : int { TR_POST = 0, TR_CLAIM = 1, TR_PARSED = 2, TR_COPIED = 3, TR_CQE = 4, TR_SEEN = 5 };
+__device__ __forceinline__ void trace_stamp(QpDev* qp, unsigned long long idx, int which) {
+  if (qp->trace_on) qp->trace[((idx & ((1ull << qp->sq_log) - 1)) << 3) + which] = globaltimer_ns();
+}
 
 // -------------------------------------------------------------- slot reservation
 // Returns the 64-bit index of the first of `n` consecutive WQEs, or ~0ull if the
@@ -105,24 +117,35 @@ __device__ __forceinline__ void write_send_wqe(QpDev* qp, unsigned long long idx
 // -------------------------------------------------------------- doorbell
 // Publish WQEs [idx, idx+n): in index order, update the doorbell record, then ring
 // the doorbell register with the first 8 bytes of the last WQE's ctrl segment.
+// `shared` = other threads may post to this QP concurrently (then the ready_head hand-off
+// needs acquire/release); a QP driven by a single thread skips both.
+__device__ __forceinline__ void st_u64_release_scope(void* p, unsigned long long v, bool sys) {
+  if (sys) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+  else asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ int sq_submit(QpDev* qp, unsigned long long idx, uint32_t n,
-                                         unsigned long long timeout_ns = 2000000000ull) {
-  fence_sys();  // WQE bytes visible (to the NIC / engine) before anything that announces them
+                                         unsigned long long timeout_ns = 2000000000ull, bool shared = true) {
+  const bool sys = qp->sys_scope != 0;
   if (ld_u64_volatile(&qp->ready_head) != idx) {
     unsigned long long t0 = globaltimer_ns();
     while (ld_u64_volatile(&qp->ready_head) != idx) {
       if (globaltimer_ns() - t0 > timeout_ns) return WAIT_TIMEOUT;
     }
   }
+  if (shared) fence_scope(sys);  // acquire the previous poster's doorbell: ours must land after it
   unsigned long long last = idx + n - 1;
   st_u32_volatile(&qp->dbr[DBR_SND], be32((uint32_t)((last + 1) & 0xffff)));
-  fence_sys();  // doorbell record before doorbell register
   unsigned long long db = (unsigned long long)ctrl_word0(OP_NOP, (uint16_t)last) |
                           ((unsigned long long)ctrl_word1(qp->qpn, 0) << 32);
-  // The opcode byte in the doorbell copy is informational; the engine and a real
-  // BlueFlame register both key on wqe_index + qpn.
-  st_u64_release(qp->bf, db);
-  st_u64_release(&qp->ready_head, idx + n);
+  // The doorbell register store is a RELEASE: WQE bytes and the doorbell record are
+  // visible before it (what the engine audits, and what a ConnectX requires: it may fetch
+  // the record and the WQE as soon as the MMIO write lands).
+  st_u64_release_scope(qp->bf, db, sys);
+  trace_stamp(qp, idx, TR_POST);
+  // Hand the queue to the next poster only after our doorbell is visible, otherwise two
+  // doorbells could land out of order and leave the register pointing at the older index.
+  if (shared) st_u64_release_scope(&qp->ready_head, idx + n, sys);
+  else st_u64_relaxed(&qp->ready_head, idx + n);
   return WAIT_OK;
 }
 
@@ -145,6 +168,7 @@ __device__ __forceinline__ int cq_poll_once(QpDev* qp) {
   unsigned long long cons = ld_u64_volatile(&qp->sq_cons);
   unsigned long long done = cons + (unsigned long long)((uint16_t)(wqe_counter + 1 - (uint16_t)cons));
   if (atomicCAS(&cq->ci, ci, ci + 1) == ci) {
+    trace_stamp(qp, done - 1, TR_SEEN);
     atomicMax(&qp->sq_cons, done);
     st_u32_volatile(&cq->dbrec[0], be32((ci + 1) & 0xffffff));
   }

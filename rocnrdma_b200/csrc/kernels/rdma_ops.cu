@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(32, 1) rdma_stream_kernel(StreamArgs a) {
       write_send_wqe(qp, idx, OP_SEND, lbase + off, a.lkey, a.bytes, flags);
     else
       write_rdma_wqe(qp, idx, (uint8_t)a.opcode, lbase + off, a.lkey, rbase + off, a.rkey, a.bytes, flags);
-    if (sq_submit(qp, idx, 1, a.timeout_ns) != WAIT_OK) { status = WAIT_TIMEOUT; break; }
+    if (sq_submit(qp, idx, 1, a.timeout_ns, /*shared=*/false) != WAIT_OK) { status = WAIT_TIMEOUT; break; }
     last = idx;
     ++done;
   }
