@@ -77,6 +77,12 @@ _SIGS = {
     "rn_engine_stats": (i32, [vp, C.POINTER(RnEngineStats)]),
     "rn_hca_scratch": (u64, [vp, C.POINTER(u64)]),
     "rn_hca_work_stream": (u64, [vp]),
+    "rn_hca_aux_stream": (u64, [vp]),
+    "rn_hca_dev_scratch": (u64, [vp, C.POINTER(u64)]),
+    "rn_pack_record_bytes": (u64, [u64]),
+    "rn_pack_tile_elems": (u32, []),
+    "rn_k_pack_fp8_write": (i32, [u64, i32, u64, u64, u64, u32, u64, u64, u32, u64, u32, u32, u32, u64, u64, u64]),
+    "rn_k_unpack_fp8": (i32, [u64, i32, u64, u64, u64, u32, u64, u64, u64, u64]),
     "rn_k_rdma_stream": (i32, [u64, C.POINTER(u64), u32, u32, u64, u32, u64, u32, u64, u32, u32, u32, u32, u64, u32, u64, u64]),
     "rn_wire_build_wqe": (None, [C.POINTER(u8), u32, u32, u32, u64, u32, u64, u32, u32, u32, u32]),
     "rn_wire_decode_cqe": (i32, [C.POINTER(u8), C.POINTER(RnWc)]),

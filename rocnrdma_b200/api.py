@@ -206,6 +206,25 @@ class Context:
         self._scratch_ptr = self._lib.rn_hca_scratch(self._h, C.byref(sz))
         self._scratch_size = sz.value
 
+    @property
+    def aux_stream(self):
+        """A second pre-created non-blocking stream (consumer kernels that must run
+        concurrently with a producer on ``stream``).  Like ``stream`` it exists before any
+        engine runs, because creating a stream stalls behind a resident engine."""
+        if getattr(self, "_aux", None) is None:
+            import torch
+            self._aux = torch.cuda.ExternalStream(self._lib.rn_hca_aux_stream(self._h), device=self.device)
+        return self._aux
+
+    def dev_scratch(self, nbytes: int, offset: int = 0) -> int:
+        """Address inside the HCA's zero-initialised device scratch (kernel counters; every
+        kernel that uses it leaves it zeroed again)."""
+        sz = C.c_uint64()
+        base = self._lib.rn_hca_dev_scratch(self._h, C.byref(sz))
+        if offset + nbytes > sz.value:
+            raise ValueError("device scratch request too large")
+        return base + offset
+
     def scratch(self, nbytes: int, offset: int = 0):
         """(address, ctypes view) of the HCA's mapped pinned result area.  Kernels write
         their status/timing words here and the host reads them after a stream sync, so the

@@ -1,13 +1,17 @@
 // The softhca DMA engine: a persistent sm_100a kernel that plays the HCA.
 //
-// Each engine CTA scans the doorbell registers of the QP table, claims either the
-// prologue of the next un-parsed WQE (decode, MKey checks, address translation,
-// receive-WQE matching) or one chunk of an already-parsed WQE, moves the chunk
-// with a TMA bulk-copy pipeline (cp.async.bulk global->shared->global, one
-// issuing thread, mbarrier-tracked, no LSU traffic), and retires WQEs strictly in
-// order by writing mlx5 CQEs.  Messages therefore fan out over every engine CTA
-// (large transfers run at HBM / NVLink speed) while small messages cost one
-// doorbell poll + one prologue.
+// Pipeline per QP (every stage can be on a different CTA, many WQEs in flight):
+//   claim    one CAS on the claim head hands WQE w to a CTA (the doorbell bounds it)
+//   parse    that CTA reads + decodes the WQE and translates both MKeys -- in parallel
+//            with the CTAs parsing w-1, w+1, ...
+//   commit   a short ordered section (parse_seq turn): QP-error flush, receive-WQE
+//            matching for SEND / WRITE_IMM, publish resolved[w], arm the chunk ticket
+//   move     TMA bulk-copy pipeline (cp.async.bulk global->shared->global, one issuing
+//            thread, mbarrier-tracked, no LSU traffic); a multi-chunk WQE is offered to
+//            idle CTAs through a fetch-add ticket, its owner keeps drawing from it too
+//   retire   strictly in order: mlx5 CQEs are written under a per-QP retire lock
+// Large transfers fan out over every engine CTA (HBM / NVLink speed); small messages
+// cost one claim + one ordered hand-off each and pipeline across CTAs.
 //
 // Failure handling mirrors an RC QP: a bad key / bounds / opcode produces an error
 // CQE with an IB syndrome, moves the QP to ERR and flushes later WQEs; a missing
@@ -190,12 +194,16 @@ __device__ __forceinline__ void copy_generic(uint64_t src, uint64_t dst, uint32_
   }
 }
 
-// ------------------------------------------------------------------ prologue
-// Parse WQE `w` of `qp`, fill resolved[slot].  Returns false when the WQE must be
-// retried later (receiver not ready).
-__device__ __forceinline__ bool prologue(EngineCtl* ctl, QpDev* qp, unsigned long long w) {
+// ------------------------------------------------------------------ parse + commit
+struct Parsed {
+  WqeView v;
+  uint64_t src, dst;
+  uint8_t syn;
+};
+
+// Parallel part: runs concurrently for neighbouring WQEs of the same QP.
+__device__ __forceinline__ void parse_wqe(QpDev* qp, unsigned long long w, Parsed* p) {
   const uint32_t mask = (1u << qp->sq_log) - 1;
-  Resolved* r = qp->resolved + (w & mask);
   const uint8_t* slot = qp->sq + ((w & mask) << 6);
   Wqe64 wqe;
   uint4* wv = reinterpret_cast<uint4*>(&wqe);
@@ -203,68 +211,46 @@ __device__ __forceinline__ bool prologue(EngineCtl* ctl, QpDev* qp, unsigned lon
   wv[1] = ld_v4_volatile(slot + 16);
   wv[2] = ld_v4_volatile(slot + 32);
   wv[3] = ld_v4_volatile(slot + 48);
-  WqeView v;
-  uint8_t syn = SYN_OK;
-  uint64_t src = 0, dst = 0;
-  uint64_t rq_idx = 0;
-  uint8_t rq_taken = 0;
-  bool ok = decode_wqe(&wqe, &v);
-  if (qp->state == QPS_ERR) {
-    syn = SYN_WR_FLUSH_ERR;
-  } else if (!ok || v.qpn != qp->qpn || v.wqe_idx != (uint16_t)w) {
-    syn = SYN_LOCAL_QP_OP_ERR;
+  p->syn = SYN_OK;
+  p->src = p->dst = 0;
+  bool ok = decode_wqe(&wqe, &p->v);
+  WqeView& v = p->v;
+  if (!ok || v.qpn != qp->qpn || v.wqe_idx != (uint16_t)w) {
+    p->syn = SYN_LOCAL_QP_OP_ERR;
   } else if (!qp->r.connected && v.opcode != OP_NOP) {
-    syn = SYN_LOCAL_QP_OP_ERR;
+    p->syn = SYN_LOCAL_QP_OP_ERR;
   } else {
     switch (v.opcode) {
       case OP_NOP: v.bytes = 0; break;
       case OP_RDMA_WRITE:
       case OP_RDMA_WRITE_IMM:
-        src = translate(qp->lkeys, qp->n_lkeys, v.lkey, v.laddr, v.bytes, 0, false, &syn);
-        if (src) dst = translate(qp->r.rkeys, qp->r.n_rkeys, v.rkey, v.raddr, v.bytes, ACC_REMOTE_WRITE, true, &syn);
+        p->src = translate(qp->lkeys, qp->n_lkeys, v.lkey, v.laddr, v.bytes, 0, false, &p->syn);
+        if (p->src) p->dst = translate(qp->r.rkeys, qp->r.n_rkeys, v.rkey, v.raddr, v.bytes, ACC_REMOTE_WRITE, true, &p->syn);
         break;
       case OP_RDMA_READ:
-        dst = translate(qp->lkeys, qp->n_lkeys, v.lkey, v.laddr, v.bytes, ACC_LOCAL_WRITE, false, &syn);
-        if (dst) src = translate(qp->r.rkeys, qp->r.n_rkeys, v.rkey, v.raddr, v.bytes, ACC_REMOTE_READ, true, &syn);
+        p->dst = translate(qp->lkeys, qp->n_lkeys, v.lkey, v.laddr, v.bytes, ACC_LOCAL_WRITE, false, &p->syn);
+        if (p->dst) p->src = translate(qp->r.rkeys, qp->r.n_rkeys, v.rkey, v.raddr, v.bytes, ACC_REMOTE_READ, true, &p->syn);
         break;
       case OP_SEND:
       case OP_SEND_IMM:
-        src = translate(qp->lkeys, qp->n_lkeys, v.lkey, v.laddr, v.bytes, 0, false, &syn);
+        p->src = translate(qp->lkeys, qp->n_lkeys, v.lkey, v.laddr, v.bytes, 0, false, &p->syn);
         break;
-      default: syn = SYN_LOCAL_QP_OP_ERR;
-    }
-    bool needs_recv = (syn == SYN_OK) &&
-                      (v.opcode == OP_SEND || v.opcode == OP_SEND_IMM || v.opcode == OP_RDMA_WRITE_IMM);
-    if (needs_recv) {
-      // match against the responder's receive queue
-      uint32_t rpi16 = be32(ld_u32_volatile(&qp->r.rq_dbr[DBR_RCV])) & 0xffff;
-      unsigned long long head = qp->rq_head;
-      if (((rpi16 - (uint32_t)head) & 0xffff) == 0) {
-        unsigned long long now = globaltimer_ns();
-        if (qp->rnr_since == 0) { qp->rnr_since = now; atomicAdd(&qp->n_rnr, 1ull); }
-        if (now - qp->rnr_since < ctl->rnr_timeout_ns) return false;  // retry later
-        syn = SYN_RNR_RETRY_EXC_ERR;
-      } else {
-        fence_scope(qp->sys_scope != 0);
-        const uint8_t* rs = qp->r.rq + ((head & ((1ull << qp->r.rq_log) - 1)) << 4);
-        uint4 d = ld_v4_volatile(rs);
-        uint32_t rbytes = be32(d.x) & 0x7fffffffu, rlkey = be32(d.y);
-        uint64_t raddr = ((uint64_t)be32(d.z) << 32) | be32(d.w);
-        rq_idx = head;
-        rq_taken = 1;
-        qp->rq_head = head + 1;
-        if (v.opcode != OP_RDMA_WRITE_IMM) {
-          if (rbytes < v.bytes) syn = SYN_REMOTE_INVAL_REQ_ERR;
-          else dst = translate(qp->r.rkeys, qp->r.n_rkeys, rlkey, raddr, v.bytes, ACC_LOCAL_WRITE, true, &syn);
-        }
-      }
-      qp->rnr_since = 0;
+      default: p->syn = SYN_LOCAL_QP_OP_ERR;
     }
   }
-  // Work granule: at least the QP's chunk_bytes, grown so that a large message is cut
-  // into ~4 claims per engine CTA.  Claims serialise on one atomic (~1 us each), so a
-  // fixed 128 KiB granule caps a 1 GiB write near 130 GB/s (measured); this keeps the
-  // claim rate negligible while still load-balancing the tail.
+}
+
+__device__ __forceinline__ bool needs_recv_wqe(uint8_t opcode) {
+  return opcode == OP_SEND || opcode == OP_SEND_IMM || opcode == OP_RDMA_WRITE_IMM;
+}
+
+// Publish resolved[w].  Runs in the parallel part for plain RDMA WRITE / READ / NOP and in
+// the ordered part for receive-consuming opcodes.  Returns the number of chunks.
+__device__ __forceinline__ uint32_t write_resolved(QpDev* qp, unsigned long long w, const WqeView& v, uint8_t syn,
+                                                   uint64_t src, uint64_t dst, uint64_t rq_idx, uint8_t rq_taken) {
+  Resolved* r = qp->resolved + (w & ((1u << qp->sq_log) - 1));
+  // Work granule: at least the QP's chunk_bytes, grown so that a very large message is cut
+  // into ~8 claims per engine CTA (bounded claim traffic, still balances the tail).
   uint32_t chunk = qp->chunk_bytes;
   {
     uint32_t target = 8u * gridDim.x;
@@ -282,10 +268,38 @@ __device__ __forceinline__ bool prologue(EngineCtl* ctl, QpDev* qp, unsigned lon
   r->rq_idx = rq_idx;
   r->done = 0;
   *(volatile unsigned long long*)&r->state = (w << 2) | 1ull;
-  if (syn != SYN_OK && syn != SYN_WR_FLUSH_ERR) qp->state = QPS_ERR;
-  atomicAdd(&qp->n_wqe, 1ull);
-  trace_stamp(qp, w, TR_PARSED);
-  return true;
+  return nchunks;
+}
+
+// Receive matching: only ever executed by the turn holder, i.e. in WQE order.  May block
+// (bounded by rnr_timeout_ns) on a receiver that has not posted a buffer yet -- which is
+// exactly what RC does to the WQEs queued behind it.
+__device__ __forceinline__ void match_recv(EngineCtl* ctl, QpDev* qp, const WqeView& v, uint8_t* syn, uint64_t* dst,
+                                           uint64_t* rq_idx, uint8_t* rq_taken) {
+  unsigned long long head = qp->rq_head;
+  unsigned long long t0 = 0;
+  bool have = false;
+  for (;;) {
+    uint32_t rpi16 = be32(ld_u32_volatile(&qp->r.rq_dbr[DBR_RCV])) & 0xffff;
+    if (((rpi16 - (uint32_t)head) & 0xffff) != 0) { have = true; break; }
+    unsigned long long now = globaltimer_ns();
+    if (t0 == 0) { t0 = now; atomicAdd(&qp->n_rnr, 1ull); }
+    if (now - t0 > ctl->rnr_timeout_ns || *ctl->stop) break;
+    __nanosleep(500);
+  }
+  if (!have) { *syn = SYN_RNR_RETRY_EXC_ERR; return; }
+  fence_scope(qp->sys_scope != 0);
+  const uint8_t* rs = qp->r.rq + ((head & ((1ull << qp->r.rq_log) - 1)) << 4);
+  uint4 d = ld_v4_volatile(rs);
+  uint32_t rbytes = be32(d.x) & 0x7fffffffu, rlkey = be32(d.y);
+  uint64_t raddr = ((uint64_t)be32(d.z) << 32) | be32(d.w);
+  *rq_idx = head;
+  *rq_taken = 1;
+  qp->rq_head = head + 1;
+  if (v.opcode != OP_RDMA_WRITE_IMM) {
+    if (rbytes < v.bytes) *syn = SYN_REMOTE_INVAL_REQ_ERR;
+    else *dst = translate(qp->r.rkeys, qp->r.n_rkeys, rlkey, raddr, v.bytes, ACC_LOCAL_WRITE, true, syn);
+  }
 }
 
 // ------------------------------------------------------------------ retire
@@ -313,6 +327,7 @@ __device__ __forceinline__ void retire(QpDev* qp) {
         qp->n_cqe = qp->n_cqe + 1;          // counters are only written under the retire lock
       }
       if (err) qp->n_err = qp->n_err + 1;
+      qp->n_wqe = qp->n_wqe + 1;
       qp->n_bytes = qp->n_bytes + r->bytes;
       ++h;
     }
@@ -331,66 +346,111 @@ struct Work {
   uint32_t chunk;
 };
 
-__device__ __forceinline__ bool try_claim(EngineCtl* ctl, QpDev* qp, Work* out, bool* saw_pending) {
-  if (qp->state != QPS_RTS && qp->state != QPS_ERR) return false;
-  const bool sys = qp->sys_scope != 0;
-  unsigned long long cur = ld_u64_volatile(&qp->cursor);
-  unsigned long long w = cur >> CURSOR_CHUNK_BITS;
-  const uint32_t ph = (uint32_t)(cur & CURSOR_PHASE_MASK);
-  if (ph == PH_LOCKED) { *saw_pending = true; return false; }
-  const uint32_t mask = (1u << qp->sq_log) - 1;
-  if (ph == PH_UNPARSED) {
-    unsigned long long db = ld_u64_volatile(qp->bf);
-    uint32_t idx16 = (be32((uint32_t)db) >> 8) & 0xffff;
-    uint32_t pending = (idx16 + 1 - (uint32_t)w) & 0xffff;
-    if (pending == 0) return false;
-    *saw_pending = true;
-    if (atomicCAS(&qp->cursor, cur, (w << CURSOR_CHUNK_BITS) | PH_LOCKED) != cur) return false;
-    fence_scope(sys);  // acquire: WQE bytes the doorbell announced
-    trace_stamp(qp, w, TR_CLAIM);
-    // ordering audit: the doorbell record must already cover what the register announced
-    uint32_t dbr16 = be32(ld_u32_volatile(&qp->dbr[DBR_SND])) & 0xffff;
-    if (((dbr16 - (uint32_t)w) & 0xffff) < pending && ((dbr16 - (uint32_t)w) & 0xffff) < 0x8000)
-      atomicAdd(&qp->n_db_order_violations, 1ull);
-    if (!prologue(ctl, qp, w)) {
-      // receiver not ready: hand the WQE back (the one legal backwards move; nothing else
-      // can touch the cursor while it is PH_LOCKED)
-      atomicExch(&qp->cursor, w << CURSOR_CHUNK_BITS);
-      return false;
-    }
-    Resolved* res = qp->resolved + (w & mask);
-    uint32_t n = res->nchunks;
-    if (n == 1) {
-      // Single-claim WQE: nobody else reads resolved[w] before retirement, so no ticket and
-      // no release fence -- just move the queue on (fire-and-forget RED, no round trip).
-      atomicMax(&qp->cursor, (w + 1) << CURSOR_CHUNK_BITS);
-      out->qp = qp; out->w = w; out->chunk = 0;
-      return true;
-    }
-    fence_gpu();  // release: resolved[] fields before the ticket that lets others read them
-    // Every cursor move from here on is an atomicMax, so it does not matter whether the
-    // ticket or the cursor becomes visible first: a draw on a not-yet-armed ticket sees the
-    // previous WQE's exhausted one, and a straggler that draws the last chunk early can only
-    // push the cursor forward.
-    st_u64_relaxed(&res->ticket, TICKET_ONE | ((w & TICKET_FIELD_MASK) << TICKET_GEN_SHIFT) | n);
-    atomicMax(&qp->cursor, (w << CURSOR_CHUNK_BITS) | PH_OFFER);
-    out->qp = qp; out->w = w; out->chunk = 0;
-    return true;
-  }
-  // PH_OFFER: chunks of WQE w are on offer.  One fetch-add = one claim; the returned word
-  // carries (chunk, generation, nchunks), so a straggler that hits a recycled slot still
-  // holds a valid claim on whatever WQE the slot describes now.
-  *saw_pending = true;
-  Resolved* res = qp->resolved + (w & mask);
+// Draw one chunk from the ticket of the WQE in slot `res`.  `w_hint` is any index whose
+// low 20 bits are close to the real one (used to rebuild the full index).
+__device__ __forceinline__ bool draw_chunk(QpDev* qp, Resolved* res, unsigned long long w_hint, Work* out) {
+  unsigned long long peek = ld_u64_volatile(&res->ticket);
+  if ((uint32_t)(peek >> 40) >= (uint32_t)(peek & TICKET_FIELD_MASK)) return false;   // exhausted: no atomic
   unsigned long long t = atomicAdd(&res->ticket, (unsigned long long)TICKET_ONE);
   uint32_t c = (uint32_t)(t >> 40), gen = (uint32_t)((t >> TICKET_GEN_SHIFT) & TICKET_FIELD_MASK);
   uint32_t n = (uint32_t)(t & TICKET_FIELD_MASK);
-  if (c >= n) { __nanosleep(100); return false; }
-  unsigned long long wfull = w + ((gen - (uint32_t)w) & TICKET_FIELD_MASK);
-  if (c + 1 == n) atomicMax(&qp->cursor, (wfull + 1) << CURSOR_CHUNK_BITS);
-  fence_gpu();  // acquire: resolved[] fields of the generation this ticket names
-  out->qp = qp; out->w = wfull; out->chunk = c;
+  if (c >= n) return false;
+  // the ticket names its own WQE (generation), so a draw on a recycled slot is still a
+  // valid claim on whatever WQE lives there now
+  long long delta = (long long)((gen - (uint32_t)w_hint) & TICKET_FIELD_MASK);
+  if (delta >= (long long)(TICKET_FIELD_MASK + 1) / 2) delta -= (long long)(TICKET_FIELD_MASK + 1);
+  fence_gpu();  // acquire: resolved[] fields of that generation
+  out->qp = qp; out->w = (unsigned long long)((long long)w_hint + delta); out->chunk = c;
   return true;
+}
+
+__device__ __forceinline__ bool try_claim(EngineCtl* ctl, QpDev* qp, Work* out, bool* saw_pending) {
+  const uint32_t st = qp->state;
+  if (st != QPS_RTS && st != QPS_ERR) return false;
+  const bool sys = qp->sys_scope != 0;
+  const uint32_t mask = (1u << qp->sq_log) - 1;
+  // four independent loads, one round trip
+  unsigned long long c = ld_u64_volatile(&qp->cursor);
+  unsigned long long db = ld_u64_volatile(qp->bf);
+  unsigned long long off = ld_u64_volatile(&qp->offer);
+  unsigned long long ps = ld_u64_volatile(&qp->parse_seq) & ~PARSE_ERR_BIT;
+  uint32_t idx16 = (be32((uint32_t)db) >> 8) & 0xffff;
+  uint32_t pending = (idx16 + 1 - (uint32_t)c) & 0xffff;
+  if (pending != 0 && pending < 0x8000) {
+    *saw_pending = true;
+    if (atomicCAS(&qp->cursor, c, c + 1) == c) {
+      const unsigned long long w = c;
+      fence_scope(sys);  // acquire: WQE bytes the doorbell announced
+      trace_stamp(qp, w, TR_CLAIM);
+      // ordering audit: the doorbell record must already cover what the register announced
+      uint32_t dbr16 = be32(ld_u32_volatile(&qp->dbr[DBR_SND])) & 0xffff;
+      if (((dbr16 - (uint32_t)w) & 0xffff) < pending && ((dbr16 - (uint32_t)w) & 0xffff) < 0x8000)
+        atomicAdd(&qp->n_db_order_violations, 1ull);
+      // ---- parallel part
+      Parsed p;
+      parse_wqe(qp, w, &p);
+      const bool recv = p.syn == SYN_OK && needs_recv_wqe(p.v.opcode);
+      uint32_t n = 1;
+      if (!recv) n = write_resolved(qp, w, p.v, p.syn, p.src, p.dst, 0, 0);
+      // ---- ordered part: wait for the turn.  The turn word also carries "QP already failed",
+      //      so the common path is one poll + one store, no fence.
+      unsigned long long turn = ld_u64_volatile(&qp->parse_seq);
+      if ((turn & ~PARSE_ERR_BIT) != w) {
+        unsigned long long t0 = globaltimer_ns();
+        while (((turn = ld_u64_volatile(&qp->parse_seq)) & ~PARSE_ERR_BIT) != w) {
+          if (globaltimer_ns() - t0 > 4000000000ull) { ctl->fatal = 2; break; }   // predecessor died
+        }
+      }
+      bool err = (turn & PARSE_ERR_BIT) != 0 || st == QPS_ERR;
+      uint8_t syn = p.syn;
+      if (err) {
+        // flushed: nothing moves, whatever the parse said
+        syn = SYN_WR_FLUSH_ERR;
+        n = write_resolved(qp, w, p.v, syn, 0, 0, 0, 0);
+      } else if (recv) {
+        fence_gpu();  // acquire rq_head from the previous receive-consuming WQE
+        uint64_t dst = p.dst, rq_idx = 0;
+        uint8_t rq_taken = 0;
+        match_recv(ctl, qp, p.v, &syn, &dst, &rq_idx, &rq_taken);
+        n = write_resolved(qp, w, p.v, syn, p.src, dst, rq_idx, rq_taken);
+        fence_gpu();  // release rq_head
+      }
+      if (syn != SYN_OK && !err) { qp->state = QPS_ERR; err = true; }
+      Resolved* res = qp->resolved + (w & mask);
+      const unsigned long long next = (w + 1) | (err ? (unsigned long long)PARSE_ERR_BIT : 0ull);
+      if (n > 1) {
+        fence_gpu();  // release resolved[w] before the ticket that lets helpers read it
+        st_u64_relaxed(&res->ticket, TICKET_ONE | ((w & TICKET_FIELD_MASK) << TICKET_GEN_SHIFT) | n);
+        st_u64_release_scope(&qp->parse_seq, next, false);   // helpers trust: committed => ticket armed
+      } else {
+        st_u64_relaxed(&qp->parse_seq, next);
+      }
+      trace_stamp(qp, w, TR_PARSED);
+      out->qp = qp; out->w = w; out->chunk = 0;
+      return true;
+    }
+  }
+  // ---- help, oldest first: retirement is in order, so the head WQE's chunks matter most
+  if (off < ps) {
+    unsigned long long o = off;
+    for (int step = 0; step < 8 && o < ps; ++step) {
+      Resolved* res = qp->resolved + (o & mask);
+      unsigned long long t = ld_u64_volatile(&res->ticket);
+      const bool mine = (uint32_t)((t >> TICKET_GEN_SHIFT) & TICKET_FIELD_MASK) == (uint32_t)(o & TICKET_FIELD_MASK);
+      if (mine && (uint32_t)(t >> 40) < (uint32_t)(t & TICKET_FIELD_MASK)) {
+        if (draw_chunk(qp, res, o, out)) {
+          if (o > off) atomicMax(&qp->offer, o);
+          *saw_pending = true;
+          return true;
+        }
+        continue;   // lost the race for the last chunks: look again
+      }
+      ++o;          // single-chunk WQE or fully drawn: move the window
+    }
+    if (o > off) atomicMax(&qp->offer, o);
+  }
+  if (ld_u64_volatile(&qp->retire_head) != c) *saw_pending = true;   // work in flight somewhere
+  return false;
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -411,6 +471,8 @@ __global__ void __launch_bounds__(kThreads, 1) engine_kernel(EngineCtl* ctl) {
   unsigned long long last_activity = globaltimer_ns();
   uint32_t rr = blockIdx.x;
   unsigned spins = 0;
+  QpDev* sticky_qp = nullptr;        // multi-chunk WQE this CTA last worked on: keep drawing from it
+  unsigned long long sticky_w = 0;
   for (;;) {
     if (threadIdx.x == 0) {
       s.have_work = 0;
@@ -419,6 +481,12 @@ __global__ void __launch_bounds__(kThreads, 1) engine_kernel(EngineCtl* ctl) {
       if (blockIdx.x == 0) {
         ctl->n_polls = ctl->n_polls + 1;
         if (n) { ctl->dbg_last_db = ld_u64_volatile(ctl->qps[0]->bf); ctl->dbg_last_state = ctl->qps[0]->state; }
+      }
+      if (sticky_qp) {
+        Resolved* sr = sticky_qp->resolved + (sticky_w & ((1u << sticky_qp->sq_log) - 1));
+        // a successful draw is a claim that MUST be executed, whichever generation it names
+        if (draw_chunk(sticky_qp, sr, sticky_w, &work)) s.have_work = 1;
+        else sticky_qp = nullptr;
       }
       for (uint32_t k = 0; k < n && !s.have_work; ++k) {
         QpDev* qp = *(QpDev* volatile*)&ctl->qps[(rr + k) % n];   // table grows while we run
@@ -435,6 +503,7 @@ __global__ void __launch_bounds__(kThreads, 1) engine_kernel(EngineCtl* ctl) {
         s.len = bytes == 0 ? 0 : (uint32_t)((bytes - off < chunk) ? (bytes - off) : chunk);
         s.src = r->src + off;
         s.dst = r->dst + off;
+        if (*(volatile uint32_t*)&r->nchunks > 1) { sticky_qp = work.qp; sticky_w = work.w; }
         last_activity = globaltimer_ns();
         spins = 0;
       } else {

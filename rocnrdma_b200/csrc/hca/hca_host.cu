@@ -73,7 +73,7 @@ struct Qp {
 
 struct Hca {
   int dev = 0;
-  cudaStream_t ctl = nullptr, eng = nullptr, work = nullptr;
+  cudaStream_t ctl = nullptr, eng = nullptr, work = nullptr, aux = nullptr;
   uint8_t *arena = nullptr, *harena = nullptr;
   size_t arena_size = 0, arena_off = 0, harena_size = 0, harena_off = 0;
   uint32_t max_mkeys = 0;
@@ -83,6 +83,8 @@ struct Hca {
   volatile uint32_t* h_stop = nullptr;
   uint8_t* scratch = nullptr;          // mapped pinned result area (kernels write, host reads)
   size_t scratch_size = 0;
+  uint8_t* dscratch = nullptr;         // zeroed device scratch for kernel counters (kernels self-clean)
+  size_t dscratch_size = 0;
   QpDev** d_qptab = nullptr;
   uint32_t max_qps = 0;
   std::vector<Qp*> qps;
@@ -179,6 +181,7 @@ RN_API int rn_hca_open(int dev, uint32_t max_mkeys, uint32_t max_qps, uint64_t a
   // Work stream for posters: created now because creating a stream (like any allocation)
   // is serialised behind a running persistent kernel by the driver.
   CU_OK(cudaStreamCreateWithFlags(&h->work, cudaStreamNonBlocking));
+  CU_OK(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
   h->arena_size = arena_bytes ? arena_bytes : (64ull << 20);
   h->harena_size = host_arena_bytes ? host_arena_bytes : (16ull << 20);
   CU_OK(cudaMalloc(&h->arena, h->arena_size));
@@ -193,6 +196,8 @@ RN_API int rn_hca_open(int dev, uint32_t max_mkeys, uint32_t max_qps, uint64_t a
   h->h_stop = (volatile uint32_t*)arena_alloc(h, 64, true);
   h->scratch_size = 256 << 10;
   h->scratch = (uint8_t*)arena_alloc(h, h->scratch_size, true);
+  h->dscratch_size = 1 << 20;
+  h->dscratch = (uint8_t*)arena_alloc(h, h->dscratch_size, false);
   h->mrs.resize(h->max_mkeys);
   preload_all_kernels();
   CU_OK(cudaStreamSynchronize(h->ctl));
@@ -216,11 +221,18 @@ RN_API int rn_hca_close(void* hca) {
   cudaStreamDestroy(h->ctl);
   cudaStreamDestroy(h->eng);
   cudaStreamDestroy(h->work);
+  cudaStreamDestroy(h->aux);
   delete h;
   return 0;
 }
 
+RN_API uint64_t rn_hca_dev_scratch(void* hca, uint64_t* size) {
+  Hca* h = (Hca*)hca;
+  if (size) *size = h->dscratch_size;
+  return (uint64_t)h->dscratch;
+}
 RN_API uint64_t rn_hca_work_stream(void* hca) { return (uint64_t)((Hca*)hca)->work; }
+RN_API uint64_t rn_hca_aux_stream(void* hca) { return (uint64_t)((Hca*)hca)->aux; }
 RN_API uint64_t rn_hca_scratch(void* hca, uint64_t* size) {
   Hca* h = (Hca*)hca;
   if (size) *size = h->scratch_size;
@@ -585,7 +597,7 @@ RN_API int rn_qp_query(void* qp, RnQpCounters* out) {
   out->n_wqe = d.n_wqe; out->n_cqe = d.n_cqe; out->n_err = d.n_err;
   out->n_db_order_violations = d.n_db_order_violations; out->n_bytes = d.n_bytes; out->n_rnr = d.n_rnr;
   out->resv_head = d.resv_head; out->ready_head = d.ready_head; out->sq_cons = d.sq_cons;
-  out->cursor = d.cursor; out->retire_head = d.retire_head; out->state = d.state; out->pad = 0;
+  out->cursor = d.cursor; out->retire_head = d.retire_head;  // cursor = claim head out->state = d.state; out->pad = 0;
   return 0;
 }
 

@@ -112,7 +112,9 @@ struct QpDev {
   unsigned long long sq_cons;      // every index below this is complete (from CQEs)
   unsigned long long rq_pi;        // receive WQEs posted
   // ---- engine state
-  unsigned long long cursor;       // (wqe_index << 24) | phase (PH_UNPARSED < PH_LOCKED < PH_OFFER)
+  unsigned long long cursor;       // claim head: next WQE index nobody owns yet (claimed by CAS)
+  unsigned long long parse_seq;    // ordered-commit turn: WQE index allowed to commit; bit 63 = QP already in error
+  unsigned long long offer;        // oldest WQE index that may still have undrawn chunks (helpers go oldest-first)
   unsigned long long retire_head;  // next WQE index to retire in order
   unsigned int retire_lock;
   unsigned int pad0;
@@ -122,11 +124,8 @@ struct QpDev {
   unsigned long long n_wqe, n_cqe, n_err, n_db_order_violations, n_bytes, n_rnr;
 };
 
-// cursor = (wqe_index << 24) | phase, phases ordered so that every legal move increases the
-// value and all updates can be atomicMax (a late store can never rewind the queue).
-enum : unsigned long long { CURSOR_CHUNK_BITS = 24, CURSOR_PHASE_MASK = 0xffffffull,
-                            PH_UNPARSED = 0, PH_LOCKED = 1, PH_OFFER = 2 };
 // Chunk tickets: one atomicAdd(TICKET_ONE) hands out a self-describing claim.
+enum : unsigned long long { PARSE_ERR_BIT = 1ull << 63 };
 enum : unsigned long long { TICKET_ONE = 1ull << 40, TICKET_GEN_SHIFT = 20, TICKET_FIELD_MASK = 0xfffffull };
 
 struct EngineCtl {
