@@ -220,8 +220,10 @@ RN_API int rn_hca_close(void* hca) {
   cudaFreeHost(h->harena);
   cudaStreamDestroy(h->ctl);
   cudaStreamDestroy(h->eng);
-  cudaStreamDestroy(h->work);
-  cudaStreamDestroy(h->aux);
+  // work/aux are handed to PyTorch as ExternalStreams; its allocators may still record events on
+  // them when tensors that were used there die (after close()), so they live for the process.
+  cudaStreamSynchronize(h->work);
+  cudaStreamSynchronize(h->aux);
   delete h;
   return 0;
 }
