@@ -1,0 +1,370 @@
+// K4: a tcgen05 GEMM whose epilogue feeds the wire.
+//
+//   C[M,N] (bf16) = A[M,K] (bf16, K-major) * B[N,K]^T (bf16, K-major), fp32 accumulation in TMEM.
+//
+// Persistent, warp-specialised, one CTA per SM, 192 threads:
+//   warp 0      TMA producer: cp.async.bulk.tensor 2D loads (SWIZZLE_128B) of a 128x64 A tile and a
+//               256x64 B tile per stage into a 4-stage shared-memory ring (48 KiB per stage)
+//   warp 1      MMA issuer: one elected thread issues tcgen05.mma.cta_group::1.kind::f16 128x256x16,
+//               four per k-block, accumulating into one of two 256-column TMEM buffers;
+//               tcgen05.commit releases smem stages and publishes finished accumulators
+//   warps 2-5   epilogue: tcgen05.ld 32x32b.x32 (each warp owns its 32-lane TMEM quarter), fp32 ->
+//               bf16, 64-byte row segments straight into the REGISTERED send buffer; the TMEM buffer
+//               goes back to the MMA warp so tile i+1's MMAs overlap tile i's epilogue
+//   send        tiles are scheduled N-fastest, so 128-row panels of C complete progressively; the
+//               epilogue that finishes a panel's last tile builds ONE RDMA WRITE for the panel
+//               (128 x N x 2 contiguous bytes), rings the doorbell and goes back to computing --
+//               the wire moves panel p while panels p+1.. are still being multiplied.  The last CTA
+//               posts a flush NOP and waits for its CQE, so the kernel's device time covers compute
+//               AND delivery.
+// Every mbarrier wait is bounded (a wrong descriptor must not wedge an SM for good).
+// No library GEMM anywhere on this path; the reference has no counterpart (no GPU code at all).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../hca/post.cuh"
+
+using namespace rn;
+using namespace rn::dev;
+
+#define RN_API extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16, STAGES = 4;
+constexpr int A_STAGE = BM * BK * 2, B_STAGE = BN * BK * 2;       // 16 KiB + 32 KiB
+constexpr int kThreads = 192;
+constexpr int kEpiThreads = 128;
+constexpr uint32_t kTmemCols = 512;                                // two 256-column accumulators
+constexpr unsigned long long kWaitNs = 2000000000ull;
+
+struct alignas(1024) Smem {
+  uint8_t a[STAGES][A_STAGE];
+  uint8_t b[STAGES][B_STAGE];
+  alignas(8) uint64_t full[STAGES], empty[STAGES], tfull[2], tempty[2];
+  uint32_t tmem_base;
+  volatile int abort;
+};
+
+struct GemmArgs {
+  __nv_bfloat16* c;          // send buffer, row-major, ld = N (registered)
+  uint32_t M, N, K;
+  QpDev* qp;                 // nullptr: compute only
+  uint64_t c_va;             // VA of c as registered
+  uint32_t lkey, rkey;
+  uint64_t remote_va;
+  uint32_t signal_every;
+  unsigned int* counters;    // [0..m_blks): tiles done per panel ; [m_blks]: CTAs done
+  unsigned long long* acc;   // [0] max idx+1, [1] posted, [2] ~first post time
+  unsigned long long* out;   // [status, t_start, t_end, posted, t_first_post, t_compute_end, 0, 0]
+  uint64_t timeout_ns;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t n) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(n));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* b, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(s32(b)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait; false = timed out or another role aborted.
+__device__ __forceinline__ bool mbar_wait(Smem& s, uint64_t* b, uint32_t parity) {
+  if (mbar_try(b, parity)) return true;
+  unsigned long long t0 = globaltimer_ns();
+  unsigned n = 0;
+  while (!mbar_try(b, parity)) {
+    if ((++n & 255) == 0) {
+      if (s.abort) return false;
+      if (globaltimer_ns() - t0 > kWaitNs) { s.abort = 1; return false; }
+    }
+  }
+  return true;
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(s32(smem_dst)), "l"(map), "r"(s32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, SWIZZLE_128B operand tile: 128-byte rows, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t smem_desc(const void* p) {
+  uint64_t d = (uint64_t)((s32(p) & 0x3ffff) >> 4);      // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                                  // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                        // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                                  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                                  // SWIZZLE_128B
+  return d;
+}
+// kind::f16: D=f32, A=B=bf16, both K-major, N=256, M=128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+               "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                 "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                 "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t pack_bf16(uint32_t lo_f32, uint32_t hi_f32) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(__uint_as_float(lo_f32), __uint_as_float(hi_f32));
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// ------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_send_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  Smem& s = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned long long t_start = globaltimer_ns();
+  const uint32_t m_blks = g.M / BM, n_blks = g.N / BN, k_blks = g.K / BK;
+  const uint32_t n_tiles = m_blks * n_blks;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s.tfull[i], 1); mbar_init(&s.tempty[i], 4); }
+    s.abort = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+  }
+  if (warp == 1) {   // whole warp: .sync.aligned
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&s.tmem_base)), "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s.tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (uint32_t tile = blockIdx.x; tile < n_tiles && !s.abort; tile += gridDim.x) {
+        const uint32_t m_blk = tile / n_blks, n_blk = tile % n_blks;
+        for (uint32_t kb = 0; kb < k_blks; ++kb) {
+          if (!mbar_wait(s, &s.empty[stage], phase ^ 1)) goto producer_done;
+          mbar_expect_tx(&s.full[stage], A_STAGE + B_STAGE);
+          tma_load_2d(s.a[stage], &tmap_a, &s.full[stage], (int)(kb * BK), (int)(m_blk * BM));
+          tma_load_2d(s.b[stage], &tmap_b, &s.full[stage], (int)(kb * BK), (int)(n_blk * BN));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  producer_done:
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (uint32_t tile = blockIdx.x; tile < n_tiles && !s.abort; tile += gridDim.x) {
+        if (!mbar_wait(s, &s.tempty[acc], acc_phase ^ 1)) goto mma_done;     // epilogue drained this buffer
+        tc_fence_after();
+        const uint32_t d = tmem_base + acc * BN;
+        for (uint32_t kb = 0; kb < k_blks; ++kb) {
+          if (!mbar_wait(s, &s.full[stage], phase)) goto mma_done;           // TMA landed A and B
+          tc_fence_after();
+          const uint64_t da = smem_desc(s.a[stage]), db = smem_desc(s.b[stage]);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)                               // +32 bytes along K = +2 in the address field
+            umma_f16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc, (kb | (uint32_t)k) != 0);
+          tc_commit(&s.empty[stage]);                                         // frees the smem stage when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&s.tfull[acc]);                                             // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  mma_done:
+    __syncwarp();
+  } else {
+    // ===================== epilogue (4 warps <-> 4 TMEM lane quarters)
+    const uint32_t q = warp & 3;
+    uint32_t acc = 0, acc_phase = 0;
+    const bool sys = g.qp != nullptr && g.qp->sys_scope != 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const uint32_t m_blk = tile / n_blks, n_blk = tile % n_blks;
+      if (!mbar_wait(s, &s.tfull[acc], acc_phase)) break;
+      tc_fence_after();
+      const uint32_t row = m_blk * BM + q * 32 + lane;
+      __nv_bfloat16* crow = g.c + (size_t)row * g.N + (size_t)n_blk * BN;
+      const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * BN;
+#pragma unroll 2
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+        uint4* dst = reinterpret_cast<uint4*>(crow + c * 32);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          dst[j] = make_uint4(pack_bf16(r[8 * j], r[8 * j + 1]), pack_bf16(r[8 * j + 2], r[8 * j + 3]),
+                              pack_bf16(r[8 * j + 4], r[8 * j + 5]), pack_bf16(r[8 * j + 6], r[8 * j + 7]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.tempty[acc]);                             // 4 arrivals hand the buffer back
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (g.qp != nullptr) {
+        // ---- panel accounting: the last tile of a 128-row panel sends it
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");       // all 128 rows of this tile are stored
+        if (threadIdx.x == 64) {
+          fence_gpu();
+          unsigned int old = atomicAdd(&g.counters[m_blk], 1u);
+          if (old + 1 == n_blks) {
+            fence_scope(sys);   // cumulative: covers the other CTAs' tiles of this panel
+            const uint64_t panel_bytes = (uint64_t)BM * g.N * 2, off = (uint64_t)m_blk * panel_bytes;
+            unsigned long long idx = sq_reserve(g.qp, 1, g.timeout_ns);
+            const bool sig = g.signal_every <= 1 || ((idx + 1) % g.signal_every == 0);
+            if (idx != ~0ull) {
+              write_rdma_wqe(g.qp, idx, OP_RDMA_WRITE, g.c_va + off, g.lkey, g.remote_va + off, g.rkey, (uint32_t)panel_bytes,
+                             sig ? CTRL_CQ_UPDATE : 0, m_blk);
+              if (sq_submit(g.qp, idx, 1, g.timeout_ns, true) == WAIT_OK) {
+                atomicMax(&g.acc[0], idx + 1);
+                atomicAdd(&g.acc[1], 1ull);
+                atomicMax(&g.acc[2], ~globaltimer_ns());
+              } else g.out[0] = (unsigned long long)(long long)WAIT_TIMEOUT;
+            } else g.out[0] = (unsigned long long)(long long)WAIT_TIMEOUT;
+            g.counters[m_blk] = 0;
+          }
+        }
+      }
+    }
+  }
+
+  // ===================== teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+  }
+  if (threadIdx.x == 64) {
+    if (s.abort) g.out[0] = (unsigned long long)(long long)WAIT_TIMEOUT;
+    fence_gpu();
+    unsigned int old = atomicAdd(&g.counters[m_blks], 1u);
+    if (old + 1 == gridDim.x) {
+      const unsigned long long t_compute_end = globaltimer_ns();
+      fence_gpu();
+      unsigned long long posted = ld_u64_volatile(&g.acc[1]);
+      if (g.qp != nullptr) {
+        int rc = WAIT_TIMEOUT;
+        unsigned long long fidx = sq_reserve(g.qp, 1, g.timeout_ns);
+        if (fidx != ~0ull) {
+          uint8_t* slot = g.qp->sq + ((fidx & ((1ull << g.qp->sq_log) - 1)) << 6);
+          st_v4(slot + 0, ctrl_word0(OP_NOP, (uint16_t)fidx), ctrl_word1(g.qp->qpn, 1), (uint32_t)CTRL_CQ_UPDATE << 24, 0u);
+          st_v4(slot + 16, 0u, 0u, 0u, 0u);
+          st_v4(slot + 32, 0u, 0u, 0u, 0u);
+          st_v4(slot + 48, 0u, 0u, 0u, 0u);
+          if (sq_submit(g.qp, fidx, 1, g.timeout_ns, true) == WAIT_OK) rc = sq_wait(g.qp, fidx, g.timeout_ns);
+        }
+        if (posted != m_blks && rc == WAIT_OK) rc = WAIT_TIMEOUT;
+        if (rc != WAIT_OK) g.out[0] = (unsigned long long)(long long)rc;
+      }
+      g.out[1] = t_start;
+      g.out[2] = globaltimer_ns();
+      g.out[3] = posted;
+      g.out[4] = ~ld_u64_volatile(&g.acc[2]);
+      g.out[5] = t_compute_end;
+      g.counters[m_blks] = 0;
+      g.acc[0] = 0; g.acc[1] = 0; g.acc[2] = 0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ host: tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+// row-major [rows, K] bf16, box = [box_rows, 64], 128-byte swizzle
+int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t K, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_tiled();
+  if (!fn) return -38;
+  cuuint64_t dims[2] = {K, rows};
+  cuuint64_t strides[1] = {K * 2};
+  cuuint32_t box[2] = {BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -(int)r - 2000;
+}
+
+}  // namespace
+
+RN_API uint32_t rn_gemm_tile(uint32_t* bm, uint32_t* bn, uint32_t* bk) { *bm = BM; *bn = BN; *bk = BK; return STAGES; }
+
+// counters_dev: >= (M/128 + 1) * 4 + 32 bytes of zeroed device scratch (self-cleaning), out_dev: 64 B mapped pinned.
+RN_API int rn_k_gemm_send(uint64_t stream, int grid, uint64_t a, uint64_t b, uint64_t c, uint32_t M, uint32_t N, uint32_t K,
+                          uint64_t qp_dev, uint64_t c_va, uint32_t lkey, uint64_t remote_va, uint32_t rkey,
+                          uint32_t signal_every, uint64_t counters_dev, uint64_t out_dev, uint64_t timeout_ms) {
+  if (!M || !N || !K || M % BM || N % BN || K % BK) return -22;
+  if ((a | b | c) & 15) return -22;
+  CUtensorMap ma, mb;
+  int rc = make_map(&ma, (const void*)a, M, K, BM);
+  if (!rc) rc = make_map(&mb, (const void*)b, N, K, BN);
+  if (rc) return rc;
+  GemmArgs g;
+  g.c = (__nv_bfloat16*)c; g.M = M; g.N = N; g.K = K; g.qp = (QpDev*)qp_dev; g.c_va = c_va; g.lkey = lkey; g.rkey = rkey;
+  g.remote_va = remote_va; g.signal_every = signal_every ? signal_every : 1;
+  const uint32_t m_blks = M / BM;
+  g.counters = (unsigned int*)counters_dev;
+  g.acc = (unsigned long long*)(counters_dev + (((uint64_t)m_blks + 1) * 4 + 7) / 8 * 8);
+  g.out = (unsigned long long*)out_dev;
+  g.timeout_ns = (timeout_ms ? timeout_ms : 2000) * 1000000ull;
+  unsigned long long* o = (unsigned long long*)out_dev;
+  for (int i = 0; i < 8; ++i) o[i] = 0;
+  const uint32_t n_tiles = m_blks * (N / BN);
+  if (grid <= 0) grid = 148;
+  if ((uint32_t)grid > n_tiles) grid = (int)n_tiles;
+  const size_t smem = sizeof(Smem) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_send_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return -(int)e - 1000;
+    attr_set = true;
+  }
+  gemm_send_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ma, mb, g);
+  return (int)cudaGetLastError();
+}
+
+extern "C" __attribute__((visibility("default"))) void rn_preload_gemm() {
+  cudaFuncAttributes at;
+  cudaFuncGetAttributes(&at, gemm_send_kernel);
+  cudaFuncSetAttribute(gemm_send_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Smem) + 1024));
+  encode_tiled();
+}

@@ -1,0 +1,81 @@
+"""K4 wrapper: tcgen05/TMEM/TMA bf16 GEMM whose epilogue RDMA-writes finished 128-row panels."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from .. import _native as N
+from .rdma import WAIT_STATUS, _stream_ptr, work_stream
+
+BM, BN, BK = 128, 256, 64
+
+
+@dataclass
+class GemmResult:
+    status: str
+    t_start_ns: int
+    t_end_ns: int
+    panels_posted: int
+    t_first_post_ns: int
+    t_compute_end_ns: int
+    M: int
+    N: int
+    K: int
+
+    @property
+    def ok(self) -> bool:
+        return self.status == "OK"
+
+    @property
+    def device_ns(self) -> int:
+        return self.t_end_ns - self.t_start_ns
+
+    @property
+    def tflops(self) -> float:
+        return 2.0 * self.M * self.N * self.K / max(self.device_ns, 1) / 1e3
+
+    @property
+    def wire_gbps(self) -> float:
+        return 2.0 * self.M * self.N / max(self.device_ns, 1)
+
+
+def gemm_send(ctx, a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, c_mr=None, qp=None, dst_mr=None,
+              signal_every: int = 1, grid: int = 0, timeout_ms: int = 2000, stream=None, sync: bool = True,
+              scratch_slot: int = 2):
+    """``c[M,N] = a[M,K] @ b[N,K].T`` (bf16 in/out, fp32 accumulate on the 5th-gen tensor cores).
+
+    With ``qp``/``c_mr``/``dst_mr`` every finished 128-row panel of ``c`` is RDMA-written to the same
+    offset of ``dst_mr`` from inside the kernel; the call returns when the last panel has landed.
+    Shapes must be multiples of the tile: M % 128 == 0, N % 256 == 0, K % 64 == 0.
+    """
+    for t in (a, b, c):
+        assert t.dtype == torch.bfloat16 and t.is_contiguous()
+    M, K = a.shape
+    Nn, K2 = b.shape
+    assert K == K2 and tuple(c.shape) == (M, Nn)
+    if M % BM or Nn % BN or K % BK:
+        raise ValueError(f"shape ({M},{Nn},{K}) must be a multiple of the ({BM},{BN},{BK}) tile")
+    if qp is not None and (c_mr is None or dst_mr is None):
+        raise ValueError("sending needs c_mr (registration of c) and dst_mr")
+    lib = N.load()
+    ws = work_stream(ctx, stream)
+    m_blks = M // BM
+    counters = ctx.dev_scratch((m_blks + 1) * 4 + 64, offset=scratch_slot * (256 << 10))
+    out_addr, out_view = ctx.scratch(64, offset=4096 + scratch_slot * 64)
+    rc = lib.rn_k_gemm_send(_stream_ptr(ws), grid, a.data_ptr(), b.data_ptr(), c.data_ptr(), M, Nn, K,
+                            qp.dev_ptr if qp is not None else 0, c_mr.addr if c_mr is not None else 0,
+                            c_mr.lkey if c_mr is not None else 0, dst_mr.addr if dst_mr is not None else 0,
+                            dst_mr.rkey if dst_mr is not None else 0, signal_every, counters, out_addr, timeout_ms)
+    if rc:
+        raise N.NativeError(f"gemm_send launch failed ({rc})")
+    if not sync:
+        return out_view, ws
+    ws.synchronize()
+    return parse(out_view, M, Nn, K)
+
+
+def parse(view, M, Nn, K) -> GemmResult:
+    w = (C.c_int64 * 8).from_buffer(view)
+    return GemmResult(WAIT_STATUS.get(w[0], str(w[0])), w[1], w[2], w[3], w[4], w[5], M, Nn, K)

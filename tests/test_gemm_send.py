@@ -1,0 +1,72 @@
+"""K4: tcgen05 GEMM + fused RDMA write of finished panels, vs a plain fp32 PyTorch reference."""
+import pytest
+import torch
+
+from rocnrdma_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(a, b):
+    return a.float() @ b.float().T
+
+
+def _check(c, ref, K):
+    # bf16 output: half an ulp of relative error, plus fp32 accumulation noise ~ sqrt(K) * eps
+    err = (c.float() - ref).abs()
+    tol = ref.abs() * 2.0 ** -8 + 1e-3 * (K ** 0.5)
+    assert torch.all(err <= tol), f"max err {err.max().item()} (tol at that point {tol.flatten()[err.argmax()].item()})"
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 256), (256, 512, 512), (1024, 1024, 2048), (384, 768, 192)])
+def test_gemm_compute_only_matches_fp32_reference(ctx, M, N, K):
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda:0").to(torch.bfloat16)
+    b = torch.randn(N, K, device="cuda:0").to(torch.bfloat16)
+    c = torch.zeros(M, N, device="cuda:0", dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+    r = ops.gemm_send(ctx, a, b, c)
+    assert r.ok, r.status
+    _check(c, _ref(a, b), K)
+
+
+def test_gemm_identity_exposes_layout_bugs(ctx):
+    # A = I (first 256 of K) so C must reproduce B^T's leading block exactly: catches swizzle/descriptor mistakes
+    M, N, K = 256, 256, 256
+    a = torch.eye(M, K, device="cuda:0").to(torch.bfloat16)
+    b = (torch.arange(N * K, device="cuda:0").reshape(N, K) % 251).to(torch.bfloat16)
+    c = torch.zeros(M, N, device="cuda:0", dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+    r = ops.gemm_send(ctx, a, b, c)
+    assert r.ok
+    assert torch.equal(c, b.T[:M].contiguous())
+
+
+def test_gemm_send_panels_arrive_and_match(ctx):
+    M, N, K = 1024, 1024, 1024
+    torch.manual_seed(7)
+    a = torch.randn(M, K, device="cuda:0").to(torch.bfloat16)
+    b = torch.randn(N, K, device="cuda:0").to(torch.bfloat16)
+    c = torch.zeros(M, N, device="cuda:0", dtype=torch.bfloat16)
+    d = torch.zeros_like(c)
+    cm, dm = ctx.reg_mr(c), ctx.reg_mr(d)
+    qp = ctx.loopback_qp(depth=64)
+    torch.cuda.synchronize()
+    ctx.engine_start(ctas=16, idle_timeout_ms=3000)
+    try:
+        r = ops.gemm_send(ctx, a, b, c, c_mr=cm, qp=qp, dst_mr=dm, signal_every=4, grid=64)
+    finally:
+        ctx.engine_stop()
+    assert r.ok and r.panels_posted == M // 128, r
+    _check(c, _ref(a, b), K)
+    assert torch.equal(c, d), "what arrived is not what the GEMM produced"
+    cnt = qp.counters()
+    assert cnt["n_wqe"] == M // 128 + 1 and cnt["n_err"] == 0 and cnt["n_db_order_violations"] == 0
+
+
+def test_gemm_rejects_bad_shapes(ctx):
+    a = torch.zeros(100, 64, device="cuda:0", dtype=torch.bfloat16)
+    b = torch.zeros(256, 64, device="cuda:0", dtype=torch.bfloat16)
+    c = torch.zeros(100, 256, device="cuda:0", dtype=torch.bfloat16)
+    with pytest.raises(ValueError):
+        ops.gemm_send(ctx, a, b, c)
