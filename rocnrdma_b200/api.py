@@ -274,14 +274,14 @@ class Context:
         return CompletionQueue(self, c, depth, mem)
 
     def create_qp(self, scq: CompletionQueue, rcq: Optional[CompletionQueue] = None, sq_depth: int = 256,
-                  rq_depth: int = 256, sq_mem: int = W.MEM_DEVICE, chunk_bytes: int = 128 << 10) -> QueuePair:
+                  rq_depth: int = 256, sq_mem: int = W.MEM_DEVICE, chunk_bytes: int = 512 << 10) -> QueuePair:
         q = C.c_void_p()
         rcq = rcq or scq
         N.check(self._lib.rn_create_qp(self._h, scq._c, rcq._c, sq_depth, rq_depth, sq_mem, chunk_bytes, C.byref(q)),
                 "create_qp")
         return QueuePair(self, q, scq, rcq, sq_depth, rq_depth, sq_mem)
 
-    def loopback_qp(self, depth: int = 256, mem: int = W.MEM_DEVICE, chunk_bytes: int = 128 << 10,
+    def loopback_qp(self, depth: int = 256, mem: int = W.MEM_DEVICE, chunk_bytes: int = 512 << 10,
                     cq_depth: Optional[int] = None) -> QueuePair:
         cq = self.create_cq(cq_depth or max(2 * depth, 64), mem)
         return self.create_qp(cq, cq, depth, depth, mem, chunk_bytes).connect()

@@ -34,7 +34,8 @@ using namespace rn::dev;
 
 constexpr int kThreads = 128;
 constexpr uint32_t kSub = 16384;        // bytes per TMA bulk transaction
-constexpr int kStages = 12;             // smem ring depth (12 x 16 KiB = 192 KiB in flight per SM)
+constexpr int kStages = 12;             // smem ring: 12 x 16 KiB
+constexpr int kStoresInFlight = 4;      // stages whose TMA store may still be reading smem; the other 8 hold loads in flight
 constexpr uint32_t kBulkMin = 4096;     // below this the generic path is as fast
 
 // ------------------------------------------------------------------ PTX helpers
@@ -137,12 +138,13 @@ struct Smem {
   uint32_t phase_bits;   // per-stage parity of the next wait
 };
 
-// Bulk path: thread 0 runs loads kStages-1 ahead of stores.  Requires 16-byte
-// aligned src, dst and len.
+// Bulk path: thread 0 keeps kStages-kStoresInFlight loads and kStoresInFlight stores in flight.
+// (With a single store in flight every 16 KiB step exposed the store's smem-read latency,
+// ~0.35 us, which capped a CTA near 45 GB/s.)  Requires 16-byte aligned src, dst and len.
 __device__ __forceinline__ bool copy_bulk(Smem& s, uint64_t src, uint64_t dst, uint32_t len) {
   const uint32_t nsub = (len + kSub - 1) / kSub;
   uint32_t phase_bits = s.phase_bits;
-  constexpr int P = kStages - 1;
+  constexpr int P = kStages - kStoresInFlight;
   auto sub_len = [&](uint32_t i) { return (i + 1 == nsub) ? (len - i * kSub) : kSub; };
   uint32_t issued = 0;
   for (; issued < nsub && issued < (uint32_t)P; ++issued) {
@@ -163,8 +165,9 @@ __device__ __forceinline__ bool copy_bulk(Smem& s, uint64_t src, uint64_t dst, u
     bulk_s2g((void*)(dst + (uint64_t)i * kSub), s.ring[st], sub_len(i));
     bulk_commit();
     if (issued < nsub) {
-      // stage of load `issued` was last read by store i-1: allow only store i to be pending
-      bulk_wait_read<1>();
+      // the stage of load `issued` (= i + P) was last read by store i - kStoresInFlight:
+      // stores i .. i-kStoresInFlight+1 may still be pending
+      bulk_wait_read<kStoresInFlight>();
       int ls = issued % kStages;
       mbar_expect_tx(&s.full[ls], sub_len(issued));
       bulk_g2s(s.ring[ls], (const void*)(src + (uint64_t)issued * kSub), sub_len(issued), &s.full[ls]);

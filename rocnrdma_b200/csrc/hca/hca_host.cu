@@ -438,7 +438,7 @@ RN_API int rn_create_qp(void* hca, void* scq, void* rcq, uint32_t nsq, uint32_t 
   if (ls < 1 || ls > 15 || lr < 1 || lr > 15) return fail(-22, "create_qp: queue depths must be powers of two in [2, 32768]");
   if (!scq || !rcq) return fail(-22, "create_qp: CQs required");
   if (h->qps.size() >= h->max_qps) return fail(-12, "create_qp: QP table full");
-  if (chunk_bytes == 0) chunk_bytes = 128u << 10;
+  if (chunk_bytes == 0) chunk_bytes = 512u << 10;
   if (chunk_bytes & 15) return fail(-22, "create_qp: chunk_bytes must be a multiple of 16");
   bool host = sq_mem == MEM_HOST_PINNED;
   Qp* q = new Qp();
