@@ -52,6 +52,7 @@ _SIGS = {
     "rn_hca_arena": (u64, [vp, C.POINTER(u64)]),
     "rn_classify_ptr": (i32, [u64, C.POINTER(i32)]),
     "rn_reg_mr": (i32, [vp, u64, u64, u32, C.POINTER(u32)]),
+    "rn_reg_mr_mode": (i32, [vp, u64, u64, u32, u32, C.POINTER(u32), C.POINTER(i32)]),
     "rn_mr_revoke": (i32, [vp, u32]),
     "rn_dereg_mr": (i32, [vp, u32]),
     "rn_mr_state": (i32, [vp, u32]),
@@ -74,6 +75,8 @@ _SIGS = {
     "rn_engine_running": (i32, [vp]),
     "rn_engine_start": (i32, [vp, i32, u64, u64]),
     "rn_engine_stop": (i32, [vp]),
+    "rn_engine_set_oneshot": (i32, [vp, i32]),
+    "rn_engine_wait": (i32, [vp]),
     "rn_engine_stats": (i32, [vp, C.POINTER(RnEngineStats)]),
     "rn_hca_scratch": (u64, [vp, C.POINTER(u64)]),
     "rn_hca_work_stream": (u64, [vp]),
@@ -87,6 +90,23 @@ _SIGS = {
     "rn_k_rdma_stream": (i32, [u64, C.POINTER(u64), u32, u32, u64, u32, u64, u32, u64, u32, u32, u32, u32, u64, u32, u64, u64]),
     "rn_wire_build_wqe": (None, [C.POINTER(u8), u32, u32, u32, u64, u32, u64, u32, u32, u32, u32]),
     "rn_wire_decode_cqe": (i32, [C.POINTER(u8), C.POINTER(RnWc)]),
+    "rn_gpu_page_size": (u64, []),
+    "rn_dmabuf_export": (i32, [u64, u64, C.POINTER(i32)]),
+    "rn_dmabuf_close": (i32, [i32]),
+    "rn_dmabuf_size": (C.c_int64, [i32]),
+    "rn_alloc_range": (i32, [u64, C.POINTER(u64), C.POINTER(u64)]),
+    "rn_device_caps": (i32, [i32]),
+    "rn_device_pci": (i32, [i32, C.c_char_p, i32]),
+    "rn_p2p_open": (vp, []),
+    "rn_p2p_close": (i32, [vp]),
+    "rn_p2p_is_gpu_address": (i32, [vp, u64]),
+    "rn_p2p_get_page_size": (i32, [vp, u64, u64, C.POINTER(u64)]),
+    "rn_p2p_get_pages": (i32, [vp, u64, u64, C.POINTER(u64), C.POINTER(u32), C.POINTER(u32)]),
+    "rn_p2p_put_pages": (i32, [vp, u64, u64]),
+    "rn_p2p_live_pins": (i32, [vp]),
+    "rn_p2p_pin_size": (C.c_int64, [vp, u64]),
+    "rn_p2p_peek": (i32, [vp, u64, vp, u64]),
+    "rn_p2p_poke": (i32, [vp, u64, vp, u64]),
     "rn_k_fill_random": (i32, [u64, u64, u64, u64]),
     "rn_k_fill_bf16": (i32, [u64, u64, u64, u64, C.c_float]),
     "rn_k_checksum": (i32, [u64, u64, u64, u64]),

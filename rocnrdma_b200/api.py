@@ -259,11 +259,18 @@ class Context:
         dev = C.c_int(-1)
         return ["host", "device", "pinned_host", "managed"][self._lib.rn_classify_ptr(ptr, C.byref(dev))]
 
-    def reg_mr(self, buf, nbytes=None, access: int = W.ACC_ALL, offset: int = 0) -> MemoryRegion:
+    def reg_mr(self, buf, nbytes=None, access: int = W.ACC_ALL, offset: int = 0, mode: str = "direct") -> MemoryRegion:
+        """Register ``buf`` for RDMA.  ``mode="dmabuf"`` additionally exports the range as a dma-buf
+        fd through the CUDA driver (``MemoryRegion.dmabuf_fd``) -- the handle an HCA takes in
+        ``ibv_reg_dmabuf_mr`` -- which pins the GPU pages for as long as the region lives."""
         ptr, n = _ptr_len(buf, nbytes)
         key = C.c_uint32()
-        N.check(self._lib.rn_reg_mr(self._h, ptr + offset, n, access, C.byref(key)), "reg_mr")
+        fd = C.c_int(-1)
+        m = {"direct": 0, "dmabuf": 1}[mode]
+        N.check(self._lib.rn_reg_mr_mode(self._h, ptr + offset, n, access, m, C.byref(key), C.byref(fd)), "reg_mr")
         mr = MemoryRegion(self, ptr + offset, n, key.value, access, keepalive=buf)
+        mr.dmabuf_fd = fd.value
+        mr.mode = mode
         self._mrs.append(mr)
         return mr
 
@@ -289,6 +296,17 @@ class Context:
     # ---- engine
     def engine_start(self, ctas: int = 32, idle_timeout_ms: int = 5000, rnr_timeout_ms: int = 500):
         N.check(self._lib.rn_engine_start(self._h, ctas, idle_timeout_ms, rnr_timeout_ms), "engine_start")
+
+    def engine_run_oneshot(self, ctas: int = 32):
+        """Launch the engine, let it execute everything already posted, return when it has
+        drained and exited.  For profilers (ncu serialises kernels, so a resident engine and a
+        poster can never overlap there) and for host-posted batch transfers."""
+        self._lib.rn_engine_set_oneshot(self._h, 1)
+        try:
+            N.check(self._lib.rn_engine_start(self._h, ctas, 2000, 500), "engine_start")
+            N.check(self._lib.rn_engine_wait(self._h), "engine_wait")
+        finally:
+            self._lib.rn_engine_set_oneshot(self._h, 0)
 
     def engine_stop(self):
         N.check(self._lib.rn_engine_stop(self._h), "engine_stop")

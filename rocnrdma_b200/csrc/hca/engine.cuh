@@ -512,6 +512,7 @@ __global__ void __launch_bounds__(kThreads, 1) engine_kernel(EngineCtl* ctl) {
       } else {
         ++spins;
         if (pending) last_activity = globaltimer_ns();
+        else if (ctl->oneshot && spins > 4) quit = 1;   // drained: every posted WQE has retired
         if ((spins & 63) == 0) {
           fence_gpu();  // drops stale L1 lines: host-side updates (new QPs, reconnects) become visible
           if (*ctl->stop) quit = 1;
@@ -543,7 +544,11 @@ __global__ void __launch_bounds__(kThreads, 1) engine_kernel(EngineCtl* ctl) {
     if (threadIdx.x == 0) {
       QpDev* qp = work.qp;
       Resolved* r = qp->resolved + (work.w & ((1u << qp->sq_log) - 1));
-      fence_scope(qp->sys_scope != 0);  // this chunk's bytes before the count that may complete the WQE
+      // This chunk's bytes before the count that may complete the WQE.  gpu scope is enough even
+      // when the CQ or the payload lives in host / peer memory: the retirer's system-scope
+      // fence in write_cqe() is cumulative over everything this chain of gpu-scope releases made
+      // visible to it (a sys fence per chunk cost ~2x on host-resident queues, measured).
+      fence_gpu();
       const uint32_t nch = r->nchunks;
       if (nch == 1 || atomicAdd(&r->done, 1u) + 1 == nch) {
         trace_stamp(qp, work.w, TR_COPIED);

@@ -92,6 +92,7 @@ struct Hca {
   uint32_t next_qpn = 0x100, next_cqn = 1;
   int engine_ctas = 0;
   bool engine_launched = false;
+  int oneshot = 0;
   uint64_t idle_timeout_ns = 5ull * 1000000000ull, rnr_timeout_ns = 500ull * 1000000ull;
   std::mutex mu;
 };
@@ -260,6 +261,38 @@ RN_API int rn_classify_ptr(uint64_t ptr, int* device_out) {
   return 0;
 }
 
+extern "C" int rn_dmabuf_export(uint64_t ptr, uint64_t len, int* cu_err_out) __attribute__((weak));
+extern "C" int rn_dmabuf_close(int fd) __attribute__((weak));
+
+RN_API int rn_reg_mr(void* hca, uint64_t ptr, uint64_t len, uint32_t access, uint32_t* key_out);
+
+// Registration modes: 0 = direct (software HCA translates the VA itself),
+// 1 = dmabuf (additionally export the 4 KiB-aligned range as a dma-buf fd -- the pin an HCA would be
+// given through ibv_reg_dmabuf_mr; the fd is the pin's owner and is closed on dereg / revoke).
+RN_API int rn_reg_mr_mode(void* hca, uint64_t ptr, uint64_t len, uint32_t access, uint32_t mode, uint32_t* key_out,
+                          int* dmabuf_fd_out) {
+  Hca* h = (Hca*)hca;
+  if (dmabuf_fd_out) *dmabuf_fd_out = -1;
+  int fd = -1;
+  if (mode == 1) {
+    if (!rn_dmabuf_export) return fail(-38, "reg_mr: dma-buf support not built");
+    CU_OK(cudaSetDevice(h->dev));
+    uint64_t lo = ptr & ~4095ull, hi = (ptr + len + 4095) & ~4095ull;
+    int cu = 0;
+    fd = rn_dmabuf_export(lo, hi - lo, &cu);
+    if (fd < 0) return fail(fd, "reg_mr: dma-buf export of [0x%llx, +0x%llx) failed (CUresult %d)", (unsigned long long)lo,
+                            (unsigned long long)(hi - lo), cu);
+  }
+  int rc = rn_reg_mr(hca, ptr, len, access, key_out);
+  if (rc) { if (fd >= 0) rn_dmabuf_close(fd); return rc; }
+  if (fd >= 0) {
+    std::lock_guard<std::mutex> g(h->mu);
+    h->mrs[*key_out >> 8].dmabuf_fd = fd;
+  }
+  if (dmabuf_fd_out) *dmabuf_fd_out = fd;
+  return 0;
+}
+
 RN_API int rn_reg_mr(void* hca, uint64_t ptr, uint64_t len, uint32_t access, uint32_t* key_out) {
   Hca* h = (Hca*)hca;
   std::lock_guard<std::mutex> g(h->mu);
@@ -328,6 +361,7 @@ RN_API int rn_mr_revoke(void* hca, uint32_t key) {
   rc = push(h, &h->d_mkeys[i].valid, &zero, sizeof zero);
   if (rc) return rc;
   h->mrs[i].state = MR_REVOKED;
+  if (h->mrs[i].dmabuf_fd >= 0 && rn_dmabuf_close) { rn_dmabuf_close(h->mrs[i].dmabuf_fd); h->mrs[i].dmabuf_fd = -1; }   // the pin goes with the memory
   return 0;
 }
 
@@ -344,6 +378,7 @@ RN_API int rn_dereg_mr(void* hca, uint32_t key) {
     if (rc) return rc;
     if (m.host_registered_by_us) cudaHostUnregister((void*)m.base);
   }
+  if (m.dmabuf_fd >= 0 && rn_dmabuf_close) rn_dmabuf_close(m.dmabuf_fd);
   uint8_t tag = m.tag;
   m = Mr();
   m.tag = tag;
@@ -676,6 +711,16 @@ RN_API int rn_engine_running(void* hca) {
   return 0;
 }
 
+RN_API int rn_engine_set_oneshot(void* hca, int on) { ((Hca*)hca)->oneshot = on; return 0; }
+RN_API int rn_engine_wait(void* hca) {
+  Hca* h = (Hca*)hca;
+  if (!h->engine_launched) return 0;
+  cudaSetDevice(h->dev);
+  cudaError_t e = cudaStreamSynchronize(h->eng);
+  h->engine_launched = false;
+  return e == cudaSuccess ? 0 : fail(-5, "engine wait: %s", cudaGetErrorString(e));
+}
+
 RN_API int rn_engine_start(void* hca, int n_ctas, uint64_t idle_timeout_ms, uint64_t rnr_timeout_ms) {
   Hca* h = (Hca*)hca;
   CU_OK(cudaSetDevice(h->dev));
@@ -696,6 +741,7 @@ RN_API int rn_engine_start(void* hca, int n_ctas, uint64_t idle_timeout_ms, uint
   for (auto* q : h->qps) if (q->in_engine_table) ++nq;
   c.stop = h->h_stop; c.qps = h->d_qptab; c.n_qps = nq; c.max_qps = h->max_qps;
   c.idle_timeout_ns = h->idle_timeout_ns; c.rnr_timeout_ns = h->rnr_timeout_ns;
+  c.oneshot = h->oneshot;
   int rc = push(h, h->d_ctl, &c, sizeof c);
   if (rc) return rc;
   size_t smem = eng::engine_smem_bytes();

@@ -138,7 +138,7 @@ struct EngineCtl {
   unsigned int running_ctas;       // CTAs alive (atomic)
   unsigned int exited_idle;        // set when the watchdog ended the engine
   unsigned int fatal;              // a DMA never completed; engine bailed out
-  unsigned int pad;
+  unsigned int oneshot;            // exit as soon as every queue is drained (profiling under ncu: kernels are serialised there)
   unsigned long long n_polls, n_chunks, n_bulk_chunks;
   unsigned long long dbg_last_db, dbg_t_start, dbg_t_exit, dbg_last_state;
 };

@@ -98,6 +98,67 @@ class DevBackend:
             self.fd = -1
 
 
+class UserBackend:
+    """The same verbs through the CUDA driver API (csrc/reg/p2ptest_user.cc): no kernel module needed.
+    A pin is a dma-buf export of the range; the CPU window is peek/poke through cudaMemcpy."""
+
+    def __init__(self):
+        from . import _native as N
+        self._lib = N.load()
+        self._s = self._lib.rn_p2p_open()
+
+    def is_gpu_address(self, addr: int) -> bool:
+        return bool(self._lib.rn_p2p_is_gpu_address(self._s, addr))
+
+    def get_page_size(self, addr: int, length: int) -> int:
+        out = C.c_uint64()
+        rc = self._lib.rn_p2p_get_page_size(self._s, addr, length, C.byref(out))
+        if rc:
+            raise HarnessError(-rc, os.strerror(-rc))
+        return out.value
+
+    def get_pages(self, addr: int, length: int) -> GetPages:
+        h, e, p = C.c_uint64(), C.c_uint32(), C.c_uint32()
+        rc = self._lib.rn_p2p_get_pages(self._s, addr, length, C.byref(h), C.byref(e), C.byref(p))
+        if rc:
+            raise HarnessError(-rc, os.strerror(-rc))
+        return GetPages(addr=addr, length=length, handle=h.value, entries=e.value, page_size=p.value)
+
+    def put_pages(self, addr: int, length: int) -> int:
+        return self._lib.rn_p2p_put_pages(self._s, addr, length)
+
+    def pin_size(self, handle: int) -> int:
+        return self._lib.rn_p2p_pin_size(self._s, handle)
+
+    @property
+    def live_pins(self) -> int:
+        return self._lib.rn_p2p_live_pins(self._s)
+
+    def peek(self, gpu_va: int, n: int) -> bytes:
+        buf = C.create_string_buffer(n)
+        rc = self._lib.rn_p2p_peek(self._s, gpu_va, buf, n)
+        if rc:
+            raise HarnessError(-rc, os.strerror(-rc))
+        return buf.raw
+
+    def poke(self, gpu_va: int, data: bytes):
+        rc = self._lib.rn_p2p_poke(self._s, gpu_va, data, len(data))
+        if rc:
+            raise HarnessError(-rc, os.strerror(-rc))
+
+    def close(self) -> int:
+        if self._s:
+            n = self._lib.rn_p2p_close(self._s)
+            self._s = None
+            return n
+        return 0
+
+
+def open_backend(kind: str = "auto"):
+    kind = available_backend() if kind == "auto" else kind
+    return DevBackend() if kind == "dev" else UserBackend()
+
+
 def available_backend() -> str:
     """'dev' when the kernel module is loaded and its node is reachable, else 'user'."""
     return "dev" if os.path.exists(DEVICE_PATH) and os.access(DEVICE_PATH, os.R_OK | os.W_OK) else "user"
