@@ -274,6 +274,11 @@ class Context:
         self._mrs.append(mr)
         return mr
 
+    def enable_peer(self, peer_device: int):
+        """Allow this context's GPU to reach ``peer_device``'s memory over NVLink (needed before
+        connecting a QP to a QP of a context that lives on that GPU)."""
+        N.check(self._lib.rn_hca_enable_peer(self._h, peer_device), "enable_peer")
+
     # ---- queues
     def create_cq(self, depth: int = 1024, mem: int = W.MEM_DEVICE) -> CompletionQueue:
         c = C.c_void_p()

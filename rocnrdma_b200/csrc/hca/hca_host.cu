@@ -234,6 +234,20 @@ RN_API uint64_t rn_hca_dev_scratch(void* hca, uint64_t* size) {
   if (size) *size = h->dscratch_size;
   return (uint64_t)h->dscratch;
 }
+// Let this HCA's GPU (its engine, its posters) reach memory of `peer_dev` over NVLink: MKey tables,
+// receive rings and CQs of a peer HCA live there when two GPUs are connected.
+RN_API int rn_hca_enable_peer(void* hca, int peer_dev) {
+  Hca* h = (Hca*)hca;
+  CU_OK(cudaSetDevice(h->dev));
+  if (peer_dev == h->dev) return 0;
+  int can = 0;
+  CU_OK(cudaDeviceCanAccessPeer(&can, h->dev, peer_dev));
+  if (!can) return fail(-13, "device %d cannot access device %d", h->dev, peer_dev);
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_dev, 0);
+  if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(-13, "enable peer access: %s", cudaGetErrorString(e));
+  cudaGetLastError();
+  return 0;
+}
 RN_API uint64_t rn_hca_work_stream(void* hca) { return (uint64_t)((Hca*)hca)->work; }
 RN_API uint64_t rn_hca_aux_stream(void* hca) { return (uint64_t)((Hca*)hca)->aux; }
 RN_API uint64_t rn_hca_scratch(void* hca, uint64_t* size) {
@@ -799,5 +813,71 @@ RN_API int rn_wire_decode_cqe(const uint8_t* cqe64, RnWc* out) {
   decode_cqe(&c, &v);
   out->qpn = v.qpn; out->byte_cnt = v.byte_cnt; out->imm = v.imm; out->wqe_counter = v.wqe_counter;
   out->opcode = v.opcode; out->syndrome = v.syndrome; out->wqe_opcode = v.wqe_opcode; out->is_error = v.is_error;
+  return 0;
+}
+
+// ------------------------------------------------------------------ host-driven baselines (B1 / B2 of BASELINE.md)
+#include <chrono>
+static inline uint64_t now_ns() {
+  return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// B2: the host posts (like ib_write_bw on a peermem MR): window-limited stream of `iters` work requests on a QP
+// whose rings live in pinned host memory, CQ polled by the CPU.  Returns elapsed ns through *ns_out.
+RN_API int rn_host_stream(void* qp, uint32_t opcode, uint64_t laddr, uint32_t lkey, uint64_t raddr, uint32_t rkey,
+                          uint32_t bytes, uint32_t iters, uint32_t window, uint64_t slot_stride, uint32_t nslots,
+                          uint64_t timeout_ms, uint64_t* ns_out, uint32_t* errors_out) {
+  Qp* q = (Qp*)qp;
+  if (q->sq_mem != MEM_HOST_PINNED || !q->scq->ring_host) return fail(-22, "host_stream: QP and CQ rings must be in pinned host memory");
+  if (!window || window > (1u << q->h.sq_log)) window = 1u << q->h.sq_log;
+  if (!nslots) nslots = 1;
+  uint32_t posted = 0, done = 0, errors = 0;
+  RnWc wc[32];
+  const uint64_t t0 = now_ns(), deadline = t0 + (timeout_ms ? timeout_ms : 5000) * 1000000ull;
+  while (done < iters) {
+    while (posted < iters && posted - done < window) {
+      uint64_t off = (uint64_t)(posted % nslots) * slot_stride;
+      int rc = rn_post_send(qp, opcode, laddr + off, lkey, raddr + off, rkey, bytes, CTRL_CQ_UPDATE, 0, nullptr);
+      if (rc) return rc;
+      ++posted;
+    }
+    int n = rn_poll_cq(q->scq, 32, wc);
+    if (n < 0) return n;
+    for (int i = 0; i < n; ++i) errors += wc[i].is_error;
+    done += (uint32_t)n;
+    if (!n && now_ns() > deadline) return fail(-110, "host_stream: timed out with %u/%u completions", done, iters);
+  }
+  *ns_out = now_ns() - t0;
+  if (errors_out) *errors_out = errors;
+  return 0;
+}
+
+// B1: host-staged.  Per message: cudaMemcpy D2H into a pinned bounce buffer, host-posted RDMA write between two
+// host MRs, cudaMemcpy H2D out of the second bounce buffer.  Everything the GPU-direct path exists to avoid.
+RN_API int rn_host_staged_stream(void* qp, uint64_t dev_src, uint64_t dev_dst, uint64_t host_a, uint32_t lkey_a,
+                                 uint64_t host_b, uint32_t rkey_b, uint32_t bytes, uint32_t iters, uint64_t slot_stride,
+                                 uint32_t nslots, uint64_t timeout_ms, uint64_t* ns_out) {
+  Qp* q = (Qp*)qp;
+  Hca* h = q->hca;
+  if (q->sq_mem != MEM_HOST_PINNED || !q->scq->ring_host) return fail(-22, "host_staged: QP and CQ rings must be in pinned host memory");
+  CU_OK(cudaSetDevice(h->dev));
+  if (!nslots) nslots = 1;
+  RnWc wc;
+  const uint64_t t0 = now_ns();
+  for (uint32_t i = 0; i < iters; ++i) {
+    uint64_t off = (uint64_t)(i % nslots) * slot_stride;
+    CU_OK(cudaMemcpyAsync((void*)host_a, (const void*)(dev_src + off), bytes, cudaMemcpyDeviceToHost, h->ctl));
+    CU_OK(cudaStreamSynchronize(h->ctl));
+    int rc = rn_post_send(qp, OP_RDMA_WRITE, host_a, lkey_a, host_b, rkey_b, bytes, CTRL_CQ_UPDATE, 0, nullptr);
+    if (rc) return rc;
+    const uint64_t deadline = now_ns() + (timeout_ms ? timeout_ms : 5000) * 1000000ull;
+    int n = 0;
+    while ((n = rn_poll_cq(q->scq, 1, &wc)) == 0)
+      if (now_ns() > deadline) return fail(-110, "host_staged: completion timed out");
+    if (n < 0 || wc.is_error) return fail(-5, "host_staged: error completion (syndrome 0x%x)", wc.syndrome);
+    CU_OK(cudaMemcpyAsync((void*)(dev_dst + off), (const void*)host_b, bytes, cudaMemcpyHostToDevice, h->ctl));
+    CU_OK(cudaStreamSynchronize(h->ctl));
+  }
+  *ns_out = now_ns() - t0;
   return 0;
 }

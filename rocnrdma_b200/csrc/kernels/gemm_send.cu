@@ -56,6 +56,7 @@ struct GemmArgs {
   uint32_t lkey, rkey;
   uint64_t remote_va;
   uint32_t signal_every;
+  uint32_t with_imm;         // 1: RDMA_WRITE_IMM, immediate = panel index (wakes a consumer on the receiving GPU)
   unsigned int* counters;    // [0..m_blks): tiles done per panel ; [m_blks]: CTAs done
   unsigned long long* acc;   // [0] max idx+1, [1] posted, [2] ~first post time
   unsigned long long* out;   // [status, t_start, t_end, posted, t_first_post, t_compute_end, 0, 0]
@@ -241,7 +242,7 @@ gemm_send_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             unsigned long long idx = sq_reserve(g.qp, 1, g.timeout_ns);
             const bool sig = g.signal_every <= 1 || ((idx + 1) % g.signal_every == 0);
             if (idx != ~0ull) {
-              write_rdma_wqe(g.qp, idx, OP_RDMA_WRITE, g.c_va + off, g.lkey, g.remote_va + off, g.rkey, (uint32_t)panel_bytes,
+              write_rdma_wqe(g.qp, idx, g.with_imm ? OP_RDMA_WRITE_IMM : OP_RDMA_WRITE, g.c_va + off, g.lkey, g.remote_va + off, g.rkey, (uint32_t)panel_bytes,
                              sig ? CTRL_CQ_UPDATE : 0, m_blk);
               if (sq_submit(g.qp, idx, 1, g.timeout_ns, true) == WAIT_OK) {
                 atomicMax(&g.acc[0], idx + 1);
@@ -331,7 +332,7 @@ RN_API uint32_t rn_gemm_tile(uint32_t* bm, uint32_t* bn, uint32_t* bk) { *bm = B
 // counters_dev: >= (M/128 + 1) * 4 + 32 bytes of zeroed device scratch (self-cleaning), out_dev: 64 B mapped pinned.
 RN_API int rn_k_gemm_send(uint64_t stream, int grid, uint64_t a, uint64_t b, uint64_t c, uint32_t M, uint32_t N, uint32_t K,
                           uint64_t qp_dev, uint64_t c_va, uint32_t lkey, uint64_t remote_va, uint32_t rkey,
-                          uint32_t signal_every, uint64_t counters_dev, uint64_t out_dev, uint64_t timeout_ms) {
+                          uint32_t signal_every, uint32_t with_imm, uint64_t counters_dev, uint64_t out_dev, uint64_t timeout_ms) {
   if (!M || !N || !K || M % BM || N % BN || K % BK) return -22;
   if ((a | b | c) & 15) return -22;
   CUtensorMap ma, mb;
@@ -340,7 +341,7 @@ RN_API int rn_k_gemm_send(uint64_t stream, int grid, uint64_t a, uint64_t b, uin
   if (rc) return rc;
   GemmArgs g;
   g.c = (__nv_bfloat16*)c; g.M = M; g.N = N; g.K = K; g.qp = (QpDev*)qp_dev; g.c_va = c_va; g.lkey = lkey; g.rkey = rkey;
-  g.remote_va = remote_va; g.signal_every = signal_every ? signal_every : 1;
+  g.remote_va = remote_va; g.signal_every = signal_every ? signal_every : 1; g.with_imm = with_imm;
   const uint32_t m_blks = M / BM;
   g.counters = (unsigned int*)counters_dev;
   g.acc = (unsigned long long*)(counters_dev + (((uint64_t)m_blks + 1) * 4 + 7) / 8 * 8);

@@ -90,6 +90,34 @@ RN_API int rn_k_rdma_stream(uint64_t stream, const uint64_t* qps_host, uint32_t 
   return (int)cudaGetLastError();
 }
 
+// ---------------------------------------------------------------- receive-side consumer
+// Waits on the QP's receive CQ for `n` arrivals (SEND or RDMA_WRITE_IMM), stamps each by its immediate.
+// out: [status, t_start, t_end, seen, bytes_total, 0,0,0] ; stamps[imm] = %globaltimer at observation.
+__global__ void __launch_bounds__(32, 1) recv_consume_kernel(QpDev* qp, uint32_t n, uint32_t max_imm, unsigned long long* stamps,
+                                                             unsigned long long* out, unsigned long long timeout_ns) {
+  if (threadIdx.x != 0) return;
+  const unsigned long long t0 = globaltimer_ns();
+  unsigned long long bytes = 0;
+  uint32_t seen = 0;
+  int status = WAIT_OK;
+  while (seen < n) {
+    uint32_t imm = 0;
+    long long got = recv_wait(qp, &imm, timeout_ns);
+    if (got < 0) { status = (int)got; break; }
+    if (stamps && imm < max_imm) stamps[imm] = globaltimer_ns();
+    bytes += (unsigned long long)got;
+    ++seen;
+  }
+  out[0] = (unsigned long long)(long long)status;
+  out[1] = t0; out[2] = globaltimer_ns(); out[3] = seen; out[4] = bytes;
+}
+RN_API int rn_k_recv_consume(uint64_t stream, uint64_t qp_dev, uint32_t n, uint32_t max_imm, uint64_t stamps_dev,
+                             uint64_t out_dev, uint64_t timeout_ms) {
+  recv_consume_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((QpDev*)qp_dev, n, max_imm, (unsigned long long*)stamps_dev,
+                                                          (unsigned long long*)out_dev, (timeout_ms ? timeout_ms : 2000) * 1000000ull);
+  return (int)cudaGetLastError();
+}
+
 // ---------------------------------------------------------------- K6: verification
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   x += 0x9e3779b97f4a7c15ull;
@@ -202,6 +230,7 @@ RN_API int rn_k_l2_flush(uint64_t stream, uint64_t ptr, uint64_t bytes, uint32_t
 extern "C" __attribute__((visibility("default"))) void rn_preload_rdma_ops() {
   cudaFuncAttributes a;
   cudaFuncGetAttributes(&a, rdma_stream_kernel);
+  cudaFuncGetAttributes(&a, recv_consume_kernel);
   cudaFuncGetAttributes(&a, fill_random_kernel);
   cudaFuncGetAttributes(&a, fill_bf16_kernel);
   cudaFuncGetAttributes(&a, checksum_kernel);

@@ -42,7 +42,7 @@ class GemmResult:
 
 
 def gemm_send(ctx, a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, c_mr=None, qp=None, dst_mr=None,
-              signal_every: int = 1, grid: int = 0, timeout_ms: int = 2000, stream=None, sync: bool = True,
+              signal_every: int = 1, with_imm: bool = False, grid: int = 0, timeout_ms: int = 2000, stream=None, sync: bool = True,
               scratch_slot: int = 2):
     """``c[M,N] = a[M,K] @ b[N,K].T`` (bf16 in/out, fp32 accumulate on the 5th-gen tensor cores).
 
@@ -67,7 +67,7 @@ def gemm_send(ctx, a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, c_mr=None,
     rc = lib.rn_k_gemm_send(_stream_ptr(ws), grid, a.data_ptr(), b.data_ptr(), c.data_ptr(), M, Nn, K,
                             qp.dev_ptr if qp is not None else 0, c_mr.addr if c_mr is not None else 0,
                             c_mr.lkey if c_mr is not None else 0, dst_mr.addr if dst_mr is not None else 0,
-                            dst_mr.rkey if dst_mr is not None else 0, signal_every, counters, out_addr, timeout_ms)
+                            dst_mr.rkey if dst_mr is not None else 0, signal_every, int(with_imm), counters, out_addr, timeout_ms)
     if rc:
         raise N.NativeError(f"gemm_send launch failed ({rc})")
     if not sync:

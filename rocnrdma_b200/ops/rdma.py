@@ -114,3 +114,25 @@ def compare(a: torch.Tensor, b: torch.Tensor, nbytes=None, stream=None) -> int:
 
 def l2_flush(scratch: torch.Tensor, value: int = 0, stream=None):
     N.load().rn_k_l2_flush(_stream_ptr(stream), scratch.data_ptr(), scratch.numel() * scratch.element_size(), value)
+
+
+def recv_consume(qp, n: int, max_imm: int = 0, stamps=None, timeout_ms: int = 2000, stream=None, sync: bool = True,
+                 scratch_off: int = 8192):
+    """Receive-side consumer kernel on ``qp``'s GPU: waits for ``n`` arrivals (SEND / RDMA_WRITE_IMM) on the
+    receive CQ and, if ``stamps`` (int64 tensor on that GPU) is given, stamps %globaltimer per immediate."""
+    ctx = qp.ctx
+    ws = work_stream(ctx, stream)
+    out_addr, out_view = ctx.scratch(64, offset=scratch_off)
+    rc = N.load().rn_k_recv_consume(_stream_ptr(ws), qp.dev_ptr, n, max_imm, stamps.data_ptr() if stamps is not None else 0,
+                                    out_addr, timeout_ms)
+    if rc:
+        raise N.NativeError(f"recv_consume launch failed ({rc})")
+    if not sync:
+        return out_view, ws
+    ws.synchronize()
+    return parse_recv(out_view)
+
+
+def parse_recv(view) -> dict:
+    w = (C.c_int64 * 8).from_buffer(view)
+    return dict(status=WAIT_STATUS.get(w[0], str(w[0])), device_ns=w[2] - w[1], t_start_ns=w[1], t_end_ns=w[2], seen=w[3], bytes=w[4])

@@ -1,0 +1,45 @@
+"""2-GPU paths (NVLink wire): one-sided write into a peer GPU, and config 4 (GEMM on GPU0 -> panels on GPU1)."""
+import pytest
+import torch
+
+import rocnrdma_b200 as rn
+from rocnrdma_b200 import ops, wire as W
+
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+
+
+def _need2():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+
+
+def test_write_into_peer_gpu_over_nvlink():
+    _need2()
+    ctx = rn.Context(0)
+    n = 32 << 20
+    src = torch.empty(n, dtype=torch.uint8, device="cuda:0")
+    dst = torch.zeros(n, dtype=torch.uint8, device="cuda:1")
+    ops.fill_random(src, 99)
+    ms, md = ctx.reg_mr(src), ctx.reg_mr(dst)          # peer HBM: registration enables the NVLink mapping
+    qp = ctx.loopback_qp(depth=32)
+    qp.set_flags(sys_scope=True)
+    torch.cuda.synchronize(0); torch.cuda.synchronize(1)
+    ctx.engine_start(ctas=32, idle_timeout_ms=3000)
+    try:
+        r = ops.rdma_stream(qp, W.OP_RDMA_WRITE, ms, md, n, iters=4, window=2)
+        rd = ops.rdma_stream(qp, W.OP_RDMA_READ, ms, md, 1 << 20, iters=1)
+    finally:
+        ctx.engine_stop()
+    assert r.ok and rd.ok
+    assert torch.equal(src.cpu(), dst.cpu())
+    assert r.gbps > 100, f"NVLink write only {r.gbps:.1f} GB/s"
+    ctx.close()
+
+
+def test_config4_gemm_on_gpu0_panels_land_on_gpu1():
+    _need2()
+    from rocnrdma_b200.models import sendrecv_gemm
+    res = sendrecv_gemm.run(M=1024, N=1024, K=1024, engine_ctas=16, reps=2)
+    assert res.ok, res
+    assert res.verified, "GPU1's buffer differs from what GPU0 computed"
+    assert res.consumer["seen"] == 8 and res.consumer["bytes"] == 2 * 1024 * 1024
