@@ -81,6 +81,7 @@ _SIGS = {
     "rn_engine_wait": (i32, [vp]),
     "rn_engine_stats": (i32, [vp, C.POINTER(RnEngineStats)]),
     "rn_hca_scratch": (u64, [vp, C.POINTER(u64)]),
+    "rn_set_device": (i32, [i32]),
     "rn_hca_work_stream": (u64, [vp]),
     "rn_hca_aux_stream": (u64, [vp]),
     "rn_hca_dev_scratch": (u64, [vp, C.POINTER(u64)]),

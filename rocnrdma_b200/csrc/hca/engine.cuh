@@ -102,28 +102,28 @@ __device__ __forceinline__ uint64_t translate(const MKeyEntry* tab, uint32_t n, 
 }
 
 // ------------------------------------------------------------------ CQE writer
-__device__ __forceinline__ void write_cqe(CqDev* cq, uint8_t* ring, uint8_t opcode, uint8_t wqe_opcode,
-                                          uint32_t qpn, uint16_t wqe_counter, uint32_t byte_cnt, uint32_t imm,
-                                          uint8_t syndrome, bool sys) {
-  unsigned int slot = sys ? atomicAdd_system(&cq->pi, 1u) : atomicAdd(&cq->pi, 1u);
-  uint32_t log_n = cq->log_n;
-  uint8_t* cqe = ring + ((size_t)(slot & ((1u << log_n) - 1)) << 6);
-  uint8_t owner = (uint8_t)((slot >> log_n) & 1u);
-  unsigned long long now = globaltimer_ns();
-  bool err = (opcode == CQE_REQ_ERR || opcode == CQE_RESP_ERR);
+// A CQE is published in two steps so that a whole run of completions shares one fence: the body
+// (first 48 bytes) of every CQE of the run, ONE fence, then the 16-byte tails that carry the owner bit
+// (the only word a consumer tests).  Slots are reserved with one atomic per CQ per run.
+__device__ __forceinline__ uint8_t* cqe_slot(uint8_t* ring, uint32_t log_n, unsigned int slot) {
+  return ring + ((size_t)(slot & ((1u << log_n) - 1)) << 6);
+}
+__device__ __forceinline__ void cqe_body(uint8_t* cqe, uint8_t opcode, uint32_t byte_cnt, uint32_t imm) {
+  const bool err = (opcode == CQE_REQ_ERR || opcode == CQE_RESP_ERR);
   st_v4(cqe + 0, 0u, 0u, 0u, 0u);
   st_v4(cqe + 16, 0u, 0u, 0u, 0u);
-  if (!err) {
-    st_v4(cqe + 32, 0u, be32(imm), 0u, be32(byte_cnt));
-  } else {
-    // err view: bytes 54 = vendor_err_synd, 55 = syndrome  (word at 52..55)
-    st_v4(cqe + 32, 0u, 0u, 0u, 0u);
-  }
+  if (!err) st_v4(cqe + 32, 0u, be32(imm), 0u, be32(byte_cnt));
+  else st_v4(cqe + 32, 0u, 0u, 0u, 0u);
+}
+__device__ __forceinline__ void cqe_tail(uint8_t* cqe, uint32_t log_n, unsigned int slot, uint8_t opcode, uint8_t wqe_opcode,
+                                         uint32_t qpn, uint16_t wqe_counter, uint8_t syndrome, unsigned long long now) {
+  const bool err = (opcode == CQE_REQ_ERR || opcode == CQE_RESP_ERR);
+  const uint8_t owner = (uint8_t)((slot >> log_n) & 1u);
+  // err view: byte 54 = vendor_err_synd, byte 55 = syndrome (top byte of the word at 52)
   uint32_t w48 = err ? 0u : be32((uint32_t)(now >> 32));
   uint32_t w52 = err ? ((uint32_t)syndrome << 24) : be32((uint32_t)now);
   uint32_t w56 = be32(((uint32_t)wqe_opcode << 24) | (qpn & 0xffffff));
   uint32_t w60 = (uint32_t)be16(wqe_counter) | ((uint32_t)cqe_op_own(opcode, owner) << 24);
-  fence_scope(sys);  // payload + first 48 bytes before the word that flips ownership
   st_v4(cqe + 48, w48, w52, w56, w60);
 }
 
@@ -281,16 +281,27 @@ __device__ __forceinline__ void match_recv(EngineCtl* ctl, QpDev* qp, const WqeV
                                            uint64_t* rq_idx, uint8_t* rq_taken) {
   unsigned long long head = qp->rq_head;
   unsigned long long t0 = 0;
-  bool have = false;
-  for (;;) {
+  // The responder's doorbell record and receive ring live wherever the responder does (another GPU
+  // over NVLink: ~3 us per dependent read, and this runs inside the ordered section).  So the
+  // producer count is cached and only re-read when the cache says "empty", and the receive WQE body
+  // is only fetched when the opcode actually needs the buffer it names (SEND, not WRITE_IMM).
+  bool have = head < qp->rq_cached_pi;
+  while (!have) {
     uint32_t rpi16 = be32(ld_u32_volatile(&qp->r.rq_dbr[DBR_RCV])) & 0xffff;
-    if (((rpi16 - (uint32_t)head) & 0xffff) != 0) { have = true; break; }
+    qp->rq_cached_pi = head + ((rpi16 - (uint32_t)head) & 0xffff);
+    if (head < qp->rq_cached_pi) { have = true; break; }
     unsigned long long now = globaltimer_ns();
     if (t0 == 0) { t0 = now; atomicAdd(&qp->n_rnr, 1ull); }
     if (now - t0 > ctl->rnr_timeout_ns || *ctl->stop) break;
     __nanosleep(500);
   }
   if (!have) { *syn = SYN_RNR_RETRY_EXC_ERR; return; }
+  if (v.opcode == OP_RDMA_WRITE_IMM) {       // consumes the slot, ignores its contents
+    *rq_idx = head;
+    *rq_taken = 1;
+    qp->rq_head = head + 1;
+    return;
+  }
   fence_scope(qp->sys_scope != 0);
   const uint8_t* rs = qp->r.rq + ((head & ((1ull << qp->r.rq_log) - 1)) << 4);
   uint4 d = ld_v4_volatile(rs);
@@ -299,13 +310,17 @@ __device__ __forceinline__ void match_recv(EngineCtl* ctl, QpDev* qp, const WqeV
   *rq_idx = head;
   *rq_taken = 1;
   qp->rq_head = head + 1;
-  if (v.opcode != OP_RDMA_WRITE_IMM) {
-    if (rbytes < v.bytes) *syn = SYN_REMOTE_INVAL_REQ_ERR;
-    else *dst = translate(qp->r.rkeys, qp->r.n_rkeys, rlkey, raddr, v.bytes, ACC_LOCAL_WRITE, true, syn);
-  }
+  if (rbytes < v.bytes) *syn = SYN_REMOTE_INVAL_REQ_ERR;
+  else *dst = translate(qp->r.rkeys, qp->r.n_rkeys, rlkey, raddr, v.bytes, ACC_LOCAL_WRITE, true, syn);
 }
 
 // ------------------------------------------------------------------ retire
+constexpr int kRetireBatch = 16;
+
+__device__ __forceinline__ uint8_t recv_cqe_opcode(uint8_t opc, bool err) {
+  return err ? CQE_RESP_ERR : (opc == OP_SEND ? CQE_RESP_SEND : (opc == OP_SEND_IMM ? CQE_RESP_SEND_IMM : CQE_RESP_WR_IMM));
+}
+
 __device__ __forceinline__ void retire(QpDev* qp) {
   const uint32_t mask = (1u << qp->sq_log) - 1;
   const bool sys = qp->sys_scope != 0;
@@ -314,29 +329,65 @@ __device__ __forceinline__ void retire(QpDev* qp) {
     fence_gpu();  // acquire: retire_head and slot states written by the previous holder / finishers
     unsigned long long h = ld_u64_volatile(&qp->retire_head);
     for (;;) {
-      Resolved* r = qp->resolved + (h & mask);
-      if (ld_u64_volatile(&r->state) != ((h << 2) | 2ull)) break;
-      uint8_t opc = r->opcode, syn = r->syndrome;
-      bool err = syn != SYN_OK;
-      if (r->rq_consumed && qp->r.rcq) {
-        uint8_t ropc = err ? CQE_RESP_ERR
-                           : (opc == OP_SEND ? CQE_RESP_SEND
-                                             : (opc == OP_SEND_IMM ? CQE_RESP_SEND_IMM : CQE_RESP_WR_IMM));
-        write_cqe(qp->r.rcq, qp->r.rcq_buf, ropc, 0, qp->r.qpn, (uint16_t)r->rq_idx, r->bytes, r->imm, syn, sys);
+      // ---- pass 1: how long is the run of finished WQEs, and how many CQEs does it need
+      int n = 0, n_send = 0, n_recv = 0;
+      while (n < kRetireBatch) {
+        Resolved* r = qp->resolved + ((h + n) & mask);
+        if (ld_u64_volatile(&r->state) != (((h + n) << 2) | 2ull)) break;
+        if (r->rq_consumed && qp->r.rcq) ++n_recv;
+        if (r->syndrome != SYN_OK || (r->fm_ce_se & CTRL_CQ_UPDATE)) ++n_send;
+        ++n;
       }
-      if (err || (r->fm_ce_se & CTRL_CQ_UPDATE)) {
-        write_cqe(qp->scq, qp->scq->buf, err ? CQE_REQ_ERR : CQE_REQ, opc, qp->qpn, (uint16_t)h, r->bytes, 0, syn, sys);
-        trace_stamp(qp, h, TR_CQE);
-        qp->n_cqe = qp->n_cqe + 1;          // counters are only written under the retire lock
+      if (n == 0) break;
+      // ---- one slot reservation per CQ for the whole run (a remote CQ costs a link round trip)
+      CqDev* scq = qp->scq;
+      unsigned int s_slot = 0, r_slot = 0;
+      uint32_t s_log = scq->log_n, r_log = 0;
+      if (n_send) s_slot = sys ? atomicAdd_system(&scq->pi, (unsigned)n_send) : atomicAdd(&scq->pi, (unsigned)n_send);
+      if (n_recv) { r_log = qp->r.rcq->log_n; r_slot = atomicAdd_system(&qp->r.rcq->pi, (unsigned)n_recv); }
+      // ---- pass 2: bodies
+      unsigned int si = s_slot, ri = r_slot;
+      for (int i = 0; i < n; ++i) {
+        Resolved* r = qp->resolved + ((h + i) & mask);
+        const uint8_t opc = r->opcode, syn = r->syndrome;
+        const bool err = syn != SYN_OK;
+        if (r->rq_consumed && qp->r.rcq) cqe_body(cqe_slot(qp->r.rcq_buf, r_log, ri++), recv_cqe_opcode(opc, err), r->bytes, r->imm);
+        if (err || (r->fm_ce_se & CTRL_CQ_UPDATE)) cqe_body(cqe_slot(scq->buf, s_log, si++), err ? CQE_REQ_ERR : CQE_REQ, r->bytes, 0);
       }
-      if (err) qp->n_err = qp->n_err + 1;
-      qp->n_wqe = qp->n_wqe + 1;
-      qp->n_bytes = qp->n_bytes + r->bytes;
-      ++h;
+      fence_scope(sys);  // payload (cumulative over every chunk's release) + bodies before any owner bit flips
+      // ---- pass 3: tails, counters
+      const unsigned long long now = globaltimer_ns();
+      si = s_slot; ri = r_slot;
+      unsigned long long bytes = 0;
+      unsigned n_err = 0;
+      for (int i = 0; i < n; ++i) {
+        Resolved* r = qp->resolved + ((h + i) & mask);
+        const uint8_t opc = r->opcode, syn = r->syndrome;
+        const bool err = syn != SYN_OK;
+        if (r->rq_consumed && qp->r.rcq) {
+          cqe_tail(cqe_slot(qp->r.rcq_buf, r_log, ri), r_log, ri, recv_cqe_opcode(opc, err), 0, qp->r.qpn, (uint16_t)r->rq_idx, syn, now);
+          ++ri;
+        }
+        if (err || (r->fm_ce_se & CTRL_CQ_UPDATE)) {
+          cqe_tail(cqe_slot(scq->buf, s_log, si), s_log, si, err ? CQE_REQ_ERR : CQE_REQ, opc, qp->qpn, (uint16_t)(h + i), syn, now);
+          ++si;
+          trace_stamp(qp, h + i, TR_CQE);
+        }
+        n_err += err;
+        bytes += r->bytes;
+      }
+      // counters are only ever written under the retire lock
+      qp->n_cqe = qp->n_cqe + (unsigned)n_send;
+      qp->n_err = qp->n_err + n_err;
+      qp->n_wqe = qp->n_wqe + (unsigned)n;
+      qp->n_bytes = qp->n_bytes + bytes;
+      h += (unsigned)n;
+      if (n < kRetireBatch) break;
     }
     *(volatile unsigned long long*)&qp->retire_head = h;
     fence_gpu();  // release
     atomicExch(&qp->retire_lock, 0u);
+    __threadfence();  // SC: unlock before re-checking the next slot (store-buffering pattern with finishers)
     Resolved* r = qp->resolved + (h & mask);
     if (ld_u64_volatile(&r->state) != ((h << 2) | 2ull)) return;
   }
@@ -367,18 +418,20 @@ __device__ __forceinline__ bool draw_chunk(QpDev* qp, Resolved* res, unsigned lo
   return true;
 }
 
-__device__ __forceinline__ bool try_claim(EngineCtl* ctl, QpDev* qp, Work* out, bool* saw_pending) {
+__device__ __forceinline__ bool try_claim(EngineCtl* ctl, QpDev* qp, Work* out, bool* saw_pending, bool host_watcher) {
   const uint32_t st = qp->state;
   if (st != QPS_RTS && st != QPS_ERR) return false;
   const bool sys = qp->sys_scope != 0;
   const uint32_t mask = (1u << qp->sq_log) - 1;
-  // four independent loads, one round trip
+  // independent loads, one round trip (the doorbell of a host-resident queue is a PCIe read: only
+  // the designated watcher pays it)
+  const bool look_at_doorbell = !sys || host_watcher || qp->sq_in_device;
   unsigned long long c = ld_u64_volatile(&qp->cursor);
-  unsigned long long db = ld_u64_volatile(qp->bf);
+  unsigned long long db = look_at_doorbell ? ld_u64_volatile(qp->bf) : 0ull;
   unsigned long long off = ld_u64_volatile(&qp->offer);
   unsigned long long ps = ld_u64_volatile(&qp->parse_seq) & ~PARSE_ERR_BIT;
   uint32_t idx16 = (be32((uint32_t)db) >> 8) & 0xffff;
-  uint32_t pending = (idx16 + 1 - (uint32_t)c) & 0xffff;
+  uint32_t pending = look_at_doorbell ? ((idx16 + 1 - (uint32_t)c) & 0xffff) : 0u;
   if (pending != 0 && pending < 0x8000) {
     *saw_pending = true;
     if (atomicCAS(&qp->cursor, c, c + 1) == c) {
@@ -476,6 +529,12 @@ __global__ void __launch_bounds__(kThreads, 1) engine_kernel(EngineCtl* ctl) {
   unsigned spins = 0;
   QpDev* sticky_qp = nullptr;        // multi-chunk WQE this CTA last worked on: keep drawing from it
   unsigned long long sticky_w = 0;
+  // Host-resident queues are polled for NEW work by one designated CTA only.  A GPU load from pinned
+  // host memory costs tens of microseconds on this platform; when every CTA paid it in every sweep, a
+  // device-resident QP sharing the engine saw its latency go from 11 us to 85 us, and 96 CTAs polling
+  // over PCIe starved a concurrent cudaMemcpy (0.9 GB/s).  Helping with an already-parsed WQE only
+  // touches device memory, so everybody still does that.
+  const bool host_watcher = blockIdx.x == gridDim.x - 1;
   for (;;) {
     if (threadIdx.x == 0) {
       s.have_work = 0;
@@ -493,7 +552,7 @@ __global__ void __launch_bounds__(kThreads, 1) engine_kernel(EngineCtl* ctl) {
       }
       for (uint32_t k = 0; k < n && !s.have_work; ++k) {
         QpDev* qp = *(QpDev* volatile*)&ctl->qps[(rr + k) % n];   // table grows while we run
-        if (qp && try_claim(ctl, qp, &work, &pending)) {
+        if (qp && try_claim(ctl, qp, &work, &pending, host_watcher)) {
           s.have_work = 1;
           rr = (rr + k) % n;
         }
@@ -511,12 +570,14 @@ __global__ void __launch_bounds__(kThreads, 1) engine_kernel(EngineCtl* ctl) {
         spins = 0;
       } else {
         ++spins;
+        // The host watcher is the only CTA that sees host-resident doorbells, so it alone may declare
+        // the engine idle or drained; everybody else follows quit_all.
         if (pending) last_activity = globaltimer_ns();
-        else if (ctl->oneshot && spins > 4) quit = 1;   // drained: every posted WQE has retired
+        else if (host_watcher && ctl->oneshot && spins > 4) { quit = 1; ctl->quit_all = 1; }   // drained: every posted WQE has retired
         if ((spins & 63) == 0) {
           fence_gpu();  // drops stale L1 lines: host-side updates (new QPs, reconnects) become visible
-          if (*ctl->stop) quit = 1;
-          else if (globaltimer_ns() - last_activity > ctl->idle_timeout_ns) { quit = 1; ctl->exited_idle = 1; }
+          if (*ctl->stop || *(volatile unsigned int*)&ctl->quit_all) quit = 1;
+          else if (host_watcher && globaltimer_ns() - last_activity > ctl->idle_timeout_ns) { quit = 1; ctl->exited_idle = 1; ctl->quit_all = 1; }
         }
         if (spins > 256) __nanosleep(200);
       }
@@ -554,6 +615,7 @@ __global__ void __launch_bounds__(kThreads, 1) engine_kernel(EngineCtl* ctl) {
         trace_stamp(qp, work.w, TR_COPIED);
         fence_gpu();  // observe every other chunk's count -> their bytes precede our CQE
         *(volatile unsigned long long*)&r->state = (work.w << 2) | 2ull;
+        __threadfence();  // SC: "finished" store before the retire try-lock (pairs with the unlock / re-check below)
         retire(qp);
       }
     }

@@ -248,6 +248,7 @@ RN_API int rn_hca_enable_peer(void* hca, int peer_dev) {
   cudaGetLastError();
   return 0;
 }
+RN_API int rn_set_device(int dev) { return cudaSetDevice(dev) == cudaSuccess ? 0 : -19; }
 RN_API uint64_t rn_hca_work_stream(void* hca) { return (uint64_t)((Hca*)hca)->work; }
 RN_API uint64_t rn_hca_aux_stream(void* hca) { return (uint64_t)((Hca*)hca)->aux; }
 RN_API uint64_t rn_hca_scratch(void* hca, uint64_t* size) {
@@ -498,8 +499,9 @@ RN_API int rn_create_qp(void* hca, void* scq, void* rcq, uint32_t nsq, uint32_t 
   unsigned long long* bf = (unsigned long long*)arena_alloc(h, 64, host);
   Resolved* res = (Resolved*)arena_alloc(h, (size_t)nsq * sizeof(Resolved), false);
   unsigned long long* trace = (unsigned long long*)arena_alloc(h, (size_t)nsq * 64, false);
+  uint32_t* flags = (uint32_t*)arena_alloc(h, (size_t)nsq * 4, false);
   q->d = (QpDev*)arena_alloc(h, sizeof(QpDev), false);
-  if (!sq || !rq || !dbr || !bf || !res || !trace || !q->d) { delete q; return fail(-12, "create_qp: control arena exhausted"); }
+  if (!sq || !rq || !dbr || !bf || !res || !trace || !flags || !q->d) { delete q; return fail(-12, "create_qp: control arena exhausted"); }
   memset(&q->h, 0, sizeof q->h);
   q->h.qpn = h->next_qpn++;
   q->h.state = QPS_RESET;
@@ -510,7 +512,9 @@ RN_API int rn_create_qp(void* hca, void* scq, void* rcq, uint32_t nsq, uint32_t 
   q->h.chunk_bytes = chunk_bytes;
   q->h.resolved = res;
   q->h.trace = trace;
+  q->h.ready_flags = flags;
   q->h.trace_on = 0;
+  q->h.sq_in_device = host ? 0 : 1;
   q->h.sys_scope = (host || q->scq->mem == MEM_HOST_PINNED || q->rcq->mem == MEM_HOST_PINNED) ? 1 : 0;
   // doorbell register idle value: "last posted index = 0xffff" <=> nothing posted
   unsigned long long bf0 = (unsigned long long)ctrl_word0(OP_NOP, 0xffff) | ((unsigned long long)ctrl_word1(q->h.qpn, 0) << 32);

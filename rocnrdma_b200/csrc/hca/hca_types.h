@@ -102,15 +102,20 @@ struct QpDev {
   uint32_t n_lkeys;
   uint32_t chunk_bytes;       // engine work granule for this QP
   uint32_t sys_scope;         // 1: some ring/peer of this QP is outside this GPU -> system-scope fences
+  uint32_t sq_in_device;      // 1: SQ / doorbell live in this GPU's memory (cheap to poll from every CTA)
+  uint32_t pad1;
   uint32_t trace_on;          // 1: stamp the WQE lifecycle into trace[]
   unsigned long long* trace;  // 8 x u64 per SQ slot: post, claim, parsed, copied, cqe, seen, -, -
   RemoteView r;
   Resolved* resolved;         // one per SQ slot
+  uint32_t* ready_flags;      // one per SQ slot: (index + 1) once the WQE bytes are complete (shared posters)
   // ---- device poster state
   unsigned long long resv_head;    // next WQE index to hand out
   unsigned long long ready_head;   // every index below this has rung its doorbell
   unsigned long long sq_cons;      // every index below this is complete (from CQEs)
   unsigned long long rq_pi;        // receive WQEs posted
+  unsigned int db_lock;            // try-lock: its holder rings one doorbell for every ready WQE
+  unsigned int pad2;
   // ---- engine state
   unsigned long long cursor;       // claim head: next WQE index nobody owns yet (claimed by CAS)
   unsigned long long parse_seq;    // ordered-commit turn: WQE index allowed to commit; bit 63 = QP already in error
@@ -119,7 +124,7 @@ struct QpDev {
   unsigned int retire_lock;
   unsigned int pad0;
   unsigned long long rq_head;      // next receive WQE of the *peer* to consume
-  unsigned long long rnr_since;    // globaltimer of the first receiver-not-ready for cursor WQE
+  unsigned long long rq_cached_pi; // responder receive-producer count as last read (a remote read: refreshed only when exhausted)
   // ---- counters (readable from the host; SURVEY.md section 5 "metrics")
   unsigned long long n_wqe, n_cqe, n_err, n_db_order_violations, n_bytes, n_rnr;
 };
@@ -138,6 +143,9 @@ struct EngineCtl {
   unsigned int running_ctas;       // CTAs alive (atomic)
   unsigned int exited_idle;        // set when the watchdog ended the engine
   unsigned int fatal;              // a DMA never completed; engine bailed out
+  unsigned int hint;               // bumped when there is work for more CTAs than the doorbell watchers
+  unsigned int n_watchers;         // CTAs [0, n_watchers) poll doorbells; the rest sleep on `hint`
+  unsigned int quit_all;           // a watcher found the engine idle / drained: everybody leaves
   unsigned int oneshot;            // exit as soon as every queue is drained (profiling under ncu: kernels are serialised there)
   unsigned long long n_polls, n_chunks, n_bulk_chunks;
   unsigned long long dbg_last_db, dbg_t_start, dbg_t_exit, dbg_last_state;

@@ -20,6 +20,9 @@ def _stream_ptr(stream=None) -> int:
 
 def work_stream(ctx, stream=None):
     """Stream for engine-facing kernels: never the legacy default stream (see Context.stream)."""
+    # native launchers use the calling thread's current device: make it this context's (creating a
+    # second Context, or torch work on another GPU, may have changed it)
+    N.load().rn_set_device(ctx.device)
     if stream is not None and int(stream.cuda_stream) != 0:
         return stream
     cur = torch.cuda.current_stream(ctx.device)
