@@ -82,13 +82,18 @@ _SIGS = {
     "rn_engine_stats": (i32, [vp, C.POINTER(RnEngineStats)]),
     "rn_hca_scratch": (u64, [vp, C.POINTER(u64)]),
     "rn_set_device": (i32, [i32]),
+    "rn_ipc_export": (i32, [u64, C.POINTER(u8), C.POINTER(u64), C.POINTER(u64)]),
+    "rn_ipc_open": (i32, [vp, C.POINTER(u8), C.POINTER(u64)]),
+    "rn_ipc_close": (i32, [u64]),
+    "rn_hca_alloc_remote_table": (u64, [vp, u32]),
+    "rn_hca_set_remote_mkey": (i32, [vp, u64, u32, u64, u64, u64, u32, u32]),
     "rn_hca_work_stream": (u64, [vp]),
     "rn_hca_aux_stream": (u64, [vp]),
     "rn_hca_dev_scratch": (u64, [vp, C.POINTER(u64)]),
     "rn_pack_record_bytes": (u64, [u64]),
     "rn_pack_tile_elems": (u32, []),
     "rn_k_pack_fp8_write": (i32, [u64, i32, u64, u64, u64, u32, u64, u64, u32, u64, u32, u32, u32, u64, u64, u64]),
-    "rn_k_gemm_send": (i32, [u64, i32, u64, u64, u64, u32, u32, u32, u64, u64, u32, u64, u32, u32, u32, u64, u64, u64]),
+    "rn_k_gemm_send": (i32, [u64, i32, u64, u64, u64, u32, u32, u32, u64, u64, u32, u64, u32, u32, u32, u32, u64, u64, u64]),
     "rn_k_recv_consume": (i32, [u64, u64, u32, u32, u64, u64, u64]),
     "rn_hca_enable_peer": (i32, [vp, i32]),
     "rn_k_unpack_fp8": (i32, [u64, i32, u64, u64, u64, u32, u64, u64, u64, u64]),

@@ -885,3 +885,45 @@ RN_API int rn_host_staged_stream(void* qp, uint64_t dev_src, uint64_t dev_dst, u
   *ns_out = now_ns() - t0;
   return 0;
 }
+
+// ------------------------------------------------------------------ cross-process peers (CUDA IPC over NVLink)
+extern "C" int rn_alloc_range(uint64_t ptr, uint64_t* base, uint64_t* size) __attribute__((weak));
+
+// Export the cudaMalloc allocation that contains ptr: 64-byte IPC handle + where ptr sits inside it.
+RN_API int rn_ipc_export(uint64_t ptr, uint8_t* handle64, uint64_t* alloc_base, uint64_t* alloc_size) {
+  uint64_t base = ptr, size = 0;
+  if (rn_alloc_range && rn_alloc_range(ptr, &base, &size)) return fail(-22, "ipc_export: 0x%llx is not inside a CUDA allocation", (unsigned long long)ptr);
+  cudaIpcMemHandle_t h;
+  CU_OK(cudaIpcGetMemHandle(&h, (void*)base));
+  static_assert(sizeof(h) == 64, "IPC handle size");
+  memcpy(handle64, &h, 64);
+  *alloc_base = base;
+  *alloc_size = size;
+  return 0;
+}
+RN_API int rn_ipc_open(void* hca, const uint8_t* handle64, uint64_t* mapped_base) {
+  Hca* hh = (Hca*)hca;
+  CU_OK(cudaSetDevice(hh->dev));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  CU_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *mapped_base = (uint64_t)p;
+  return 0;
+}
+RN_API int rn_ipc_close(uint64_t mapped_base) { return cudaIpcCloseMemHandle((void*)mapped_base) == cudaSuccess ? 0 : -5; }
+
+// A local mirror of a peer HCA's MKey table whose map_base fields point at OUR mappings of the peer's memory.
+RN_API uint64_t rn_hca_alloc_remote_table(void* hca, uint32_t n) {
+  Hca* h = (Hca*)hca;
+  std::lock_guard<std::mutex> g(h->mu);
+  return (uint64_t)arena_alloc(h, sizeof(MKeyEntry) * (size_t)n, false);
+}
+RN_API int rn_hca_set_remote_mkey(void* hca, uint64_t table, uint32_t idx, uint64_t base, uint64_t len, uint64_t map_base,
+                                  uint32_t key, uint32_t access) {
+  Hca* h = (Hca*)hca;
+  CU_OK(cudaSetDevice(h->dev));
+  MKeyEntry e{};
+  e.base = base; e.len = len; e.map_base = map_base; e.key = key; e.access = access; e.valid = 1; e.kind = MEM_PEER;
+  return push(h, (MKeyEntry*)table + idx, &e, sizeof e);
+}

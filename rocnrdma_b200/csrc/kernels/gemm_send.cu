@@ -21,6 +21,7 @@
 // No library GEMM anywhere on this path; the reference has no counterpart (no GPU code at all).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -57,6 +58,7 @@ struct GemmArgs {
   uint64_t remote_va;
   uint32_t signal_every;
   uint32_t with_imm;         // 1: RDMA_WRITE_IMM, immediate = panel index (wakes a consumer on the receiving GPU)
+  uint32_t out_fp8;          // 1: epilogue emits block-scaled fp8 panel records instead of bf16 rows (see below)
   unsigned int* counters;    // [0..m_blks): tiles done per panel ; [m_blks]: CTAs done
   unsigned long long* acc;   // [0] max idx+1, [1] posted, [2] ~first post time
   unsigned long long* out;   // [status, t_start, t_end, posted, t_first_post, t_compute_end, 0, 0]
@@ -133,6 +135,34 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint32_t pack_bf16(uint32_t lo_f32, uint32_t hi_f32) {
   __nv_bfloat162 v = __floats2bfloat162_rn(__uint_as_float(lo_f32), __uint_as_float(hi_f32));
   return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// fp8 output (out_fp8 = 1).  One tcgen05.ld 32x32b.x32 hands each epilogue thread 32 consecutive columns
+// of one row -- exactly one MX block -- so the block scale is a register-only reduction: amax over the
+// thread's 32 fp32 accumulators, UE8M0 exponent e (smallest power of two with amax / 2^e <= 448, the same
+// rule as the pack kernel), 32 x e4m3 = 32 bytes stored, one scale byte.  A 128-row panel becomes one
+// self-contained record   [128 x N bytes fp8, row-major][128 x N/32 scale bytes, row-major]
+// of 128*N*33/32 bytes, which is what the panel's RDMA write carries: half the wire bytes of bf16.
+__device__ __forceinline__ uint64_t panel_record_bytes(uint32_t N) { return (uint64_t)BM * N + (uint64_t)BM * (N / 32); }
+
+__device__ __forceinline__ void quantize_block(const uint32_t* r, uint4* q_out, uint8_t* scale_out) {
+  float amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) amax = fmaxf(amax, fabsf(__uint_as_float(r[i])));
+  const uint32_t vb = __float_as_uint(amax * (1.0f / 448.0f));
+  int e = (int)((vb >> 23) & 0xff) - 127 + ((vb & 0x7fffffu) ? 1 : 0);
+  e = max(-127, min(127, e));
+  const float inv = __uint_as_float((uint32_t)(127 - e) << 23);
+  uint32_t q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(__uint_as_float(r[4 * i]) * inv, __uint_as_float(r[4 * i + 1]) * inv), __NV_SATFINITE, __NV_E4M3);
+    uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(__uint_as_float(r[4 * i + 2]) * inv, __uint_as_float(r[4 * i + 3]) * inv), __NV_SATFINITE, __NV_E4M3);
+    q[i] = lo | (hi << 16);
+  }
+  q_out[0] = make_uint4(q[0], q[1], q[2], q[3]);
+  q_out[1] = make_uint4(q[4], q[5], q[6], q[7]);
+  *scale_out = (uint8_t)(e + 127);
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -212,19 +242,33 @@ gemm_send_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const uint32_t m_blk = tile / n_blks, n_blk = tile % n_blks;
       if (!mbar_wait(s, &s.tfull[acc], acc_phase)) break;
       tc_fence_after();
-      const uint32_t row = m_blk * BM + q * 32 + lane;
-      __nv_bfloat16* crow = g.c + (size_t)row * g.N + (size_t)n_blk * BN;
+      const uint32_t row_in_panel = q * 32 + lane;
+      const uint32_t row = m_blk * BM + row_in_panel;
       const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * BN;
+      if (!g.out_fp8) {
+        __nv_bfloat16* crow = g.c + (size_t)row * g.N + (size_t)n_blk * BN;
 #pragma unroll 2
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
-        tmem_ld_wait();
-        uint4* dst = reinterpret_cast<uint4*>(crow + c * 32);
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          tmem_ld_wait();
+          uint4* dst = reinterpret_cast<uint4*>(crow + c * 32);
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          dst[j] = make_uint4(pack_bf16(r[8 * j], r[8 * j + 1]), pack_bf16(r[8 * j + 2], r[8 * j + 3]),
-                              pack_bf16(r[8 * j + 4], r[8 * j + 5]), pack_bf16(r[8 * j + 6], r[8 * j + 7]));
+          for (int j = 0; j < 4; ++j)
+            dst[j] = make_uint4(pack_bf16(r[8 * j], r[8 * j + 1]), pack_bf16(r[8 * j + 2], r[8 * j + 3]),
+                                pack_bf16(r[8 * j + 4], r[8 * j + 5]), pack_bf16(r[8 * j + 6], r[8 * j + 7]));
+        }
+      } else {
+        uint8_t* rec = reinterpret_cast<uint8_t*>(g.c) + (uint64_t)m_blk * panel_record_bytes(g.N);
+        uint8_t* qrow = rec + (size_t)row_in_panel * g.N + (size_t)n_blk * BN;
+        uint8_t* srow = rec + (size_t)BM * g.N + (size_t)row_in_panel * (g.N / 32) + (size_t)n_blk * (BN / 32);
+#pragma unroll 2
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          tmem_ld_wait();
+          quantize_block(r, reinterpret_cast<uint4*>(qrow + c * 32), srow + c);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -238,7 +282,7 @@ gemm_send_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           unsigned int old = atomicAdd(&g.counters[m_blk], 1u);
           if (old + 1 == n_blks) {
             fence_scope(sys);   // cumulative: covers the other CTAs' tiles of this panel
-            const uint64_t panel_bytes = (uint64_t)BM * g.N * 2, off = (uint64_t)m_blk * panel_bytes;
+            const uint64_t panel_bytes = g.out_fp8 ? panel_record_bytes(g.N) : (uint64_t)BM * g.N * 2, off = (uint64_t)m_blk * panel_bytes;
             unsigned long long idx = sq_reserve(g.qp, 1, g.timeout_ns);
             const bool sig = g.signal_every <= 1 || ((idx + 1) % g.signal_every == 0);
             if (idx != ~0ull) {
@@ -327,12 +371,13 @@ int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t K, uint32
 
 }  // namespace
 
+RN_API uint64_t rn_gemm_panel_record_bytes(uint32_t N) { return (uint64_t)BM * N + (uint64_t)BM * (N / 32); }
 RN_API uint32_t rn_gemm_tile(uint32_t* bm, uint32_t* bn, uint32_t* bk) { *bm = BM; *bn = BN; *bk = BK; return STAGES; }
 
 // counters_dev: >= (M/128 + 1) * 4 + 32 bytes of zeroed device scratch (self-cleaning), out_dev: 64 B mapped pinned.
 RN_API int rn_k_gemm_send(uint64_t stream, int grid, uint64_t a, uint64_t b, uint64_t c, uint32_t M, uint32_t N, uint32_t K,
                           uint64_t qp_dev, uint64_t c_va, uint32_t lkey, uint64_t remote_va, uint32_t rkey,
-                          uint32_t signal_every, uint32_t with_imm, uint64_t counters_dev, uint64_t out_dev, uint64_t timeout_ms) {
+                          uint32_t signal_every, uint32_t with_imm, uint32_t out_fp8, uint64_t counters_dev, uint64_t out_dev, uint64_t timeout_ms) {
   if (!M || !N || !K || M % BM || N % BN || K % BK) return -22;
   if ((a | b | c) & 15) return -22;
   CUtensorMap ma, mb;
@@ -341,7 +386,7 @@ RN_API int rn_k_gemm_send(uint64_t stream, int grid, uint64_t a, uint64_t b, uin
   if (rc) return rc;
   GemmArgs g;
   g.c = (__nv_bfloat16*)c; g.M = M; g.N = N; g.K = K; g.qp = (QpDev*)qp_dev; g.c_va = c_va; g.lkey = lkey; g.rkey = rkey;
-  g.remote_va = remote_va; g.signal_every = signal_every ? signal_every : 1; g.with_imm = with_imm;
+  g.remote_va = remote_va; g.signal_every = signal_every ? signal_every : 1; g.with_imm = with_imm; g.out_fp8 = out_fp8;
   const uint32_t m_blks = M / BM;
   g.counters = (unsigned int*)counters_dev;
   g.acc = (unsigned long long*)(counters_dev + (((uint64_t)m_blks + 1) * 4 + 7) / 8 * 8);

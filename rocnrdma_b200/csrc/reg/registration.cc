@@ -60,7 +60,7 @@ RN_API int64_t rn_dmabuf_size(int fd) {
 
 // The allocation that contains ptr: base and size (for IPC export and for widening to page boundaries).
 RN_API int rn_alloc_range(uint64_t ptr, uint64_t* base, uint64_t* size) {
-  static GetAddressRangeFn fn = entry<GetAddressRangeFn>("cuMemGetAddressRange_v2");
+  static GetAddressRangeFn fn = entry<GetAddressRangeFn>("cuMemGetAddressRange");
   if (!fn) return -38;
   CUdeviceptr b = 0;
   size_t s = 0;

@@ -38,11 +38,38 @@ class GemmResult:
 
     @property
     def wire_gbps(self) -> float:
-        return 2.0 * self.M * self.N / max(self.device_ns, 1)
+        return 2.0 * self.M * self.N / max(self.device_ns, 1)   # bf16 panels (fp8 records carry 33/64 of this)
+
+
+def panel_record_bytes(N: int) -> int:
+    """Bytes of one fp8 panel record: 128 x N e4m3 values followed by 128 x N/32 UE8M0 scales."""
+    return BM * N + BM * (N // 32)
+
+
+def ref_fp8_panels(c_fp32: torch.Tensor) -> torch.Tensor:
+    """PyTorch reference of the fp8 epilogue: quantise an fp32 [M, N] result into panel records."""
+    from .pack import _pow2, _scale_exponent
+    M, Nn = c_fp32.shape
+    x = c_fp32.float().reshape(M, Nn // 32, 32)
+    e = _scale_exponent(x.abs().amax(dim=2))
+    q = (x * _pow2(-e)[..., None]).to(torch.float8_e4m3fn).view(torch.uint8).reshape(M, Nn)
+    sc = (e + 127).to(torch.uint8)
+    out = torch.empty(M // BM, panel_record_bytes(Nn), dtype=torch.uint8, device=c_fp32.device)
+    out[:, :BM * Nn] = q.reshape(M // BM, BM * Nn)
+    out[:, BM * Nn:] = sc.reshape(M // BM, BM * (Nn // 32))
+    return out.reshape(-1)
+
+
+def dequant_fp8_panels(rec: torch.Tensor, M: int, Nn: int) -> torch.Tensor:
+    from .pack import _pow2
+    r = rec.reshape(M // BM, panel_record_bytes(Nn))
+    q = r[:, :BM * Nn].contiguous().view(torch.float8_e4m3fn).float().reshape(M, Nn // 32, 32)
+    e = r[:, BM * Nn:].to(torch.int32).reshape(M, Nn // 32) - 127
+    return (q * _pow2(e)[..., None]).reshape(M, Nn)
 
 
 def gemm_send(ctx, a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, c_mr=None, qp=None, dst_mr=None,
-              signal_every: int = 1, with_imm: bool = False, grid: int = 0, timeout_ms: int = 2000, stream=None, sync: bool = True,
+              signal_every: int = 1, with_imm: bool = False, out_fp8: bool = False, grid: int = 0, timeout_ms: int = 2000, stream=None, sync: bool = True,
               scratch_slot: int = 2):
     """``c[M,N] = a[M,K] @ b[N,K].T`` (bf16 in/out, fp32 accumulate on the 5th-gen tensor cores).
 
@@ -50,11 +77,16 @@ def gemm_send(ctx, a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, c_mr=None,
     offset of ``dst_mr`` from inside the kernel; the call returns when the last panel has landed.
     Shapes must be multiples of the tile: M % 128 == 0, N % 256 == 0, K % 64 == 0.
     """
-    for t in (a, b, c):
+    for t in (a, b):
         assert t.dtype == torch.bfloat16 and t.is_contiguous()
     M, K = a.shape
     Nn, K2 = b.shape
-    assert K == K2 and tuple(c.shape) == (M, Nn)
+    assert K == K2 and c.is_contiguous()
+    if out_fp8:
+        # c is a uint8 buffer of M/128 panel records (block-scaled e4m3 + UE8M0 scales)
+        assert c.dtype == torch.uint8 and c.numel() >= (M // BM) * panel_record_bytes(Nn)
+    else:
+        assert c.dtype == torch.bfloat16 and tuple(c.shape) == (M, Nn)
     if M % BM or Nn % BN or K % BK:
         raise ValueError(f"shape ({M},{Nn},{K}) must be a multiple of the ({BM},{BN},{BK}) tile")
     if qp is not None and (c_mr is None or dst_mr is None):
@@ -67,7 +99,7 @@ def gemm_send(ctx, a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, c_mr=None,
     rc = lib.rn_k_gemm_send(_stream_ptr(ws), grid, a.data_ptr(), b.data_ptr(), c.data_ptr(), M, Nn, K,
                             qp.dev_ptr if qp is not None else 0, c_mr.addr if c_mr is not None else 0,
                             c_mr.lkey if c_mr is not None else 0, dst_mr.addr if dst_mr is not None else 0,
-                            dst_mr.rkey if dst_mr is not None else 0, signal_every, int(with_imm), counters, out_addr, timeout_ms)
+                            dst_mr.rkey if dst_mr is not None else 0, signal_every, int(with_imm), int(out_fp8), counters, out_addr, timeout_ms)
     if rc:
         raise N.NativeError(f"gemm_send launch failed ({rc})")
     if not sync:

@@ -70,3 +70,34 @@ def test_gemm_rejects_bad_shapes(ctx):
     c = torch.zeros(100, 256, device="cuda:0", dtype=torch.bfloat16)
     with pytest.raises(ValueError):
         ops.gemm_send(ctx, a, b, c)
+
+
+def test_gemm_fp8_epilogue_records_match_reference_and_arrive(ctx):
+    """Block-scaled fp8 send tile: the epilogue's records equal quantising the fp32 product, and they land."""
+    M, N, K = 512, 1024, 512
+    torch.manual_seed(11)
+    a = torch.randn(M, K, device="cuda:0").to(torch.bfloat16)
+    b = torch.randn(N, K, device="cuda:0").to(torch.bfloat16)
+    nb = (M // 128) * ops.panel_record_bytes(N)
+    c = torch.zeros(nb, dtype=torch.uint8, device="cuda:0")
+    d = torch.zeros(nb, dtype=torch.uint8, device="cuda:0")
+    cm, dm = ctx.reg_mr(c), ctx.reg_mr(d)
+    qp = ctx.loopback_qp(depth=64)
+    torch.cuda.synchronize()
+    ctx.engine_start(ctas=16, idle_timeout_ms=3000)
+    try:
+        r = ops.gemm_send(ctx, a, b, c, c_mr=cm, qp=qp, dst_mr=dm, out_fp8=True, grid=32)
+    finally:
+        ctx.engine_stop()
+    assert r.ok and r.panels_posted == M // 128
+    assert torch.equal(c, d), "records at the destination differ from the send buffer"
+    ref32 = _ref(a, b)
+    ref_rec = ops.ref_fp8_panels(ref32)
+    # the tensor core accumulates in a different order than the fp32 reference GEMM, so a value that
+    # sits on a rounding boundary may fall either way: allow a small fraction of 1-ulp differences,
+    # and require the dequantised result to be within the format's error bound
+    mism = (c != ref_rec).float().mean().item()
+    assert mism < 0.02, f"{mism:.4f} of the record bytes differ from the reference quantisation"
+    got = ops.dequant_fp8_panels(d, M, N)
+    blk = ref32.reshape(M, N // 32, 32).abs().amax(dim=2, keepdim=True).expand(-1, -1, 32).reshape(M, N)
+    assert torch.all((got - ref32).abs() <= blk * (2.0 ** -4) * 1.05 + 1e-2)
