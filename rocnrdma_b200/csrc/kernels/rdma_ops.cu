@@ -90,6 +90,50 @@ RN_API int rn_k_rdma_stream(uint64_t stream, const uint64_t* qps_host, uint32_t 
   return (int)cudaGetLastError();
 }
 
+// ---------------------------------------------------------------- shared-SQ stress ("many CTAs, one SQ")
+// Every CTA posts `per_cta` small RDMA writes to ONE QP through the shared (non-blocking) submit, each to
+// its own 64-byte cell; the last CTA posts the flush and waits.  Exercises slot reservation, the ready-flag
+// doorbell hand-off and in-order retirement under maximum contention.
+__global__ void __launch_bounds__(32) shared_post_stress_kernel(QpDev* qp, uint64_t laddr, uint32_t lkey, uint64_t raddr,
+                                                                uint32_t rkey, uint32_t per_cta, unsigned int* done_ctas,
+                                                                unsigned long long* out, unsigned long long timeout_ns) {
+  if (threadIdx.x != 0) return;
+  const unsigned long long t0 = globaltimer_ns();
+  int status = WAIT_OK;
+  for (uint32_t i = 0; i < per_cta; ++i) {
+    const uint64_t cell = ((uint64_t)blockIdx.x * per_cta + i) * 64;
+    unsigned long long idx = sq_reserve(qp, 1, timeout_ns);
+    if (idx == ~0ull) { status = WAIT_TIMEOUT; break; }
+    write_rdma_wqe(qp, idx, OP_RDMA_WRITE, laddr + cell, lkey, raddr + cell, rkey, 64, ((idx & 7) == 7) ? CTRL_CQ_UPDATE : 0);
+    sq_submit_shared(qp, idx, 1);
+  }
+  if (status != WAIT_OK) out[0] = (unsigned long long)(long long)status;
+  fence_gpu();
+  if (atomicAdd(done_ctas, 1u) + 1 == gridDim.x) {
+    unsigned long long fidx = sq_reserve(qp, 1, timeout_ns);
+    int rc = WAIT_TIMEOUT;
+    if (fidx != ~0ull) {
+      uint8_t* slot = qp->sq + ((fidx & ((1ull << qp->sq_log) - 1)) << 6);
+      st_v4(slot + 0, ctrl_word0(OP_NOP, (uint16_t)fidx), ctrl_word1(qp->qpn, 1), (uint32_t)CTRL_CQ_UPDATE << 24, 0u);
+      st_v4(slot + 16, 0u, 0u, 0u, 0u); st_v4(slot + 32, 0u, 0u, 0u, 0u); st_v4(slot + 48, 0u, 0u, 0u, 0u);
+      sq_submit_shared(qp, fidx, 1);
+      rc = sq_wait(qp, fidx, timeout_ns);
+    }
+    if (rc != WAIT_OK) out[0] = (unsigned long long)(long long)rc;
+    out[1] = t0; out[2] = globaltimer_ns(); out[3] = (unsigned long long)gridDim.x * per_cta;
+    *done_ctas = 0;
+  }
+}
+RN_API int rn_k_shared_post_stress(uint64_t stream, uint64_t qp_dev, int ctas, uint64_t laddr, uint32_t lkey, uint64_t raddr,
+                                   uint32_t rkey, uint32_t per_cta, uint64_t counter_dev, uint64_t out_dev, uint64_t timeout_ms) {
+  unsigned long long* o = (unsigned long long*)out_dev;
+  for (int i = 0; i < 8; ++i) o[i] = 0;
+  shared_post_stress_kernel<<<ctas, 32, 0, (cudaStream_t)stream>>>((QpDev*)qp_dev, laddr, lkey, raddr, rkey, per_cta,
+                                                                   (unsigned int*)counter_dev, (unsigned long long*)out_dev,
+                                                                   (timeout_ms ? timeout_ms : 2000) * 1000000ull);
+  return (int)cudaGetLastError();
+}
+
 // ---------------------------------------------------------------- receive-side consumer
 // Waits on the QP's receive CQ for `n` arrivals (SEND or RDMA_WRITE_IMM), stamps each by its immediate.
 // out: [status, t_start, t_end, seen, bytes_total, 0,0,0] ; stamps[imm] = %globaltimer at observation.
@@ -231,6 +275,7 @@ extern "C" __attribute__((visibility("default"))) void rn_preload_rdma_ops() {
   cudaFuncAttributes a;
   cudaFuncGetAttributes(&a, rdma_stream_kernel);
   cudaFuncGetAttributes(&a, recv_consume_kernel);
+  cudaFuncGetAttributes(&a, shared_post_stress_kernel);
   cudaFuncGetAttributes(&a, fill_random_kernel);
   cudaFuncGetAttributes(&a, fill_bf16_kernel);
   cudaFuncGetAttributes(&a, checksum_kernel);

@@ -139,3 +139,18 @@ def recv_consume(qp, n: int, max_imm: int = 0, stamps=None, timeout_ms: int = 20
 def parse_recv(view) -> dict:
     w = (C.c_int64 * 8).from_buffer(view)
     return dict(status=WAIT_STATUS.get(w[0], str(w[0])), device_ns=w[2] - w[1], t_start_ns=w[1], t_end_ns=w[2], seen=w[3], bytes=w[4])
+
+
+def shared_post_stress(qp, src_mr, dst_mr, ctas: int = 64, per_cta: int = 64, timeout_ms: int = 3000, stream=None):
+    """``ctas`` CTAs hammer one QP with ``per_cta`` 64-byte writes each through the shared submit."""
+    ctx = qp.ctx
+    ws = work_stream(ctx, stream)
+    out_addr, out_view = ctx.scratch(64, offset=12288)
+    counter = ctx.dev_scratch(64, offset=900 << 10)
+    rc = N.load().rn_k_shared_post_stress(_stream_ptr(ws), qp.dev_ptr, ctas, src_mr.addr, src_mr.lkey, dst_mr.addr, dst_mr.rkey,
+                                          per_cta, counter, out_addr, timeout_ms)
+    if rc:
+        raise N.NativeError(f"shared_post_stress launch failed ({rc})")
+    ws.synchronize()
+    w = (C.c_int64 * 8).from_buffer(out_view)
+    return dict(status=WAIT_STATUS.get(w[0], str(w[0])), device_ns=w[2] - w[1], posted=w[3])

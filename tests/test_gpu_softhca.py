@@ -164,3 +164,61 @@ def test_engine_idle_watchdog(ctx):
     time.sleep(0.6)
     assert not ctx.engine_running
     assert ctx.engine_stats()["exited_idle"] == 1
+
+
+def test_many_ctas_one_sq_stress(ctx):
+    """WQE-slot reservation / doorbell ordering under contention (128 CTAs, one SQ of 64)."""
+    ctas, per = 128, 48
+    n = ctas * per * 64
+    src, dst = _bufs(n)
+    ms, md = ctx.reg_mr(src), ctx.reg_mr(dst)
+    qp = ctx.loopback_qp(depth=64, cq_depth=128)
+    torch.cuda.synchronize()
+    ctx.engine_start(ctas=16, idle_timeout_ms=3000)
+    try:
+        r = ops.shared_post_stress(qp, ms, md, ctas=ctas, per_cta=per)
+    finally:
+        ctx.engine_stop()
+    assert r["status"] == "OK" and r["posted"] == ctas * per, r
+    assert torch.equal(src, dst)
+    c = qp.counters()
+    assert c["n_wqe"] == ctas * per + 1 and c["n_err"] == 0 and c["n_db_order_violations"] == 0, c
+    assert c["resv_head"] == c["ready_head"] == c["sq_cons"] == c["retire_head"]
+
+
+def test_rnr_retry_exceeded_when_no_receive_is_posted(ctx):
+    src, _ = _bufs(4096)
+    ms = ctx.reg_mr(src)
+    cq_a, cq_b = ctx.create_cq(64, W.MEM_HOST_PINNED), ctx.create_cq(64, W.MEM_HOST_PINNED)
+    qa = ctx.create_qp(cq_a, cq_a, 16, 16, W.MEM_HOST_PINNED)
+    qb = ctx.create_qp(cq_b, cq_b, 16, 16, W.MEM_HOST_PINNED)
+    qa.connect(qb)
+    ctx.engine_start(ctas=2, idle_timeout_ms=3000, rnr_timeout_ms=50)
+    qa.post_send(ms, 64)
+    wc = cq_a.wait(1)[0]
+    ctx.engine_stop()
+    assert wc.is_error and wc.status == "RNR_RETRY_EXC_ERR"
+    assert qa.state == "ERR" and qa.counters()["n_rnr"] >= 1
+
+
+def test_gpu_posted_send_lands_in_posted_receive_buffers(ctx):
+    n, k = 4096, 8
+    src, dst = _bufs(n * k)
+    ms, md = ctx.reg_mr(src), ctx.reg_mr(dst)
+    cq_a, cq_b = ctx.create_cq(64), ctx.create_cq(64, W.MEM_HOST_PINNED)
+    qa = ctx.create_qp(cq_a, cq_a, 16, 16)
+    qb = ctx.create_qp(cq_b, cq_b, 16, 16, W.MEM_HOST_PINNED)
+    qa.connect(qb)
+    for i in range(k):
+        qb.post_recv(md, n, off=i * n)
+    torch.cuda.synchronize()
+    ctx.engine_start(ctas=4, idle_timeout_ms=3000)
+    try:
+        r = ops.rdma_stream(qa, W.OP_SEND, ms, None, n, iters=k, window=4, slot_stride=n, nslots=k)
+        wcs = cq_b.wait(k)
+    finally:
+        ctx.engine_stop()
+    assert r.ok and r.done == [k]
+    assert all(w.opcode == W.CQE_RESP_SEND and w.byte_cnt == n for w in wcs)
+    assert [w.wqe_counter for w in wcs] == list(range(k))          # receives are consumed in order
+    assert torch.equal(src, dst)

@@ -43,3 +43,18 @@ def test_config4_gemm_on_gpu0_panels_land_on_gpu1():
     assert res.ok, res
     assert res.verified, "GPU1's buffer differs from what GPU0 computed"
     assert res.consumer["seen"] == 8 and res.consumer["bytes"] == 2 * 1024 * 1024
+
+
+def test_cross_process_ring_over_cuda_ipc(tmp_path):
+    """One process per GPU, QPs connected through parallel.connect_ring; every rank writes into the next one."""
+    _need2()
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "ring.json"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29577", os.path.join(root, "bench", "ring.py"), "--sizes", "1m,64m", "--engine-ctas", "16", "--out", str(out)]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=240, cwd=root)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    res = json.loads(out.read_text())
+    assert res["verified"] and res["world"] == 2
+    assert res["rows"][-1]["per_gpu_gbps"] > 200
