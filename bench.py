@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--msg-bytes", type=int, default=256 << 20)
     ap.add_argument("--engine-ctas", type=int, default=128)
+    ap.add_argument("--pipeline", type=int, default=8, help="steps in flight: step i is posted on QP/stream i %% pipeline")
     ap.add_argument("--extras", type=int, default=1, help="also run the fused-pack and small-message extras (untimed region)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -80,23 +81,25 @@ def main():
     host_in = torch.empty(msg, dtype=torch.uint8).pin_memory()       # e2e: step inputs live in pinned host memory
     host_in.random_(0, 255)
     ms, md = ctx.reg_mr(src), ctx.reg_mr(dst)
-    qp = ctx.loopback_qp(depth=64)
-    qp_b = ctx.loopback_qp(depth=64)        # second QP: steps ping-pong so a step's post/claim overlaps the previous copy's tail
+    depth = max(1, min(args.pipeline, 8))
+    qps = [ctx.loopback_qp(depth=64) for _ in range(depth)]   # step i goes to QP / stream i % depth: a few steps in flight,
+    qp = qps[0]                                               # like the tx-depth of ib_write_bw (one WQE and one launch per step)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
-    ev_b = torch.cuda.Event()
+    ev_tail = [torch.cuda.Event() for _ in range(depth)]
     torch.cuda.synchronize()
     barrier()
 
-    stream, stream_b = ctx.stream, ctx.aux_stream
-    out_a, out_b = ctx.scratch(64, 0), ctx.scratch(64, 64)
+    strs = ctx.streams(depth)
+    stream = strs[0]
+    outs = [ctx.scratch(64, 64 * i) for i in range(depth)]
+    out_a = outs[0]
     mr_slot = [rn.api.MemoryRegion(ctx, ms.addr + i * msg, msg, ms.key, ms.access) for i in range(nslots)]
     md_slot = [rn.api.MemoryRegion(ctx, md.addr + i * msg, msg, md.key, md.access) for i in range(nslots)]
 
     def step(i, sync=False, pingpong=True):
         s = i % nslots
-        odd = pingpong and (i & 1)
-        return ops.rdma_stream(qp_b if odd else qp, W.OP_RDMA_WRITE, mr_slot[s], md_slot[s], msg, iters=1,
-                               stream=stream_b if odd else stream, sync=sync, out=out_b if odd else out_a)
+        j = (i % depth) if pingpong else 0
+        return ops.rdma_stream(qps[j], W.OP_RDMA_WRITE, mr_slot[s], md_slot[s], msg, iters=1, stream=strs[j], sync=sync, out=outs[j])
 
     # ---------------- device-timed headline
     barrier()
@@ -106,17 +109,20 @@ def main():
         r = step(i, sync=True)
         assert r.ok, r.status
     sampler = ClockSampler(gpu_index=None, period_s=0.05).start() if rank == 0 else None
-    stream.synchronize(); stream_b.synchronize()
+    for st in strs:
+        st.synchronize()
     ev[0].record(stream)
-    stream_b.wait_event(ev[0])
+    for st in strs[1:]:
+        st.wait_event(ev[0])
     for i in range(args.steps):
         step(i)
-    ev_b.record(stream_b)
-    stream.wait_event(ev_b)
+    for j in range(1, depth):
+        ev_tail[j].record(strs[j])
+        stream.wait_event(ev_tail[j])
     ev[1].record(stream)
     ev[1].synchronize()
     dev_ms = ev[0].elapsed_time(ev[1])
-    for o in (out_a, out_b):
+    for o in outs[:min(depth, args.steps)]:
         last = ops.rdma.parse_stream_out(o[1], 1, msg)
         assert last.ok, last.status
     # H2D alone, for the e2e breakdown
@@ -197,7 +203,7 @@ def main():
             "config": {"model": "gpu_initiated_rdma_write_loopback", "msg_bytes": msg, "global_batch": world,
                        "seq_len": msg, "parallelism": f"{world}x(GPU+own HCA), loopback per GPU (BASELINE config 5 shape)",
                        "wire": "softhca device engine over HBM (no /dev/infiniband in the container; CX-7 path gated off)",
-                       "engine_ctas": args.engine_ctas, "poster": "sm_100a kernel: WQE + doorbell + device CQ poll",
+                       "engine_ctas": args.engine_ctas, "steps_in_flight": depth, "poster": "sm_100a kernel: WQE + doorbell + device CQ poll",
                        "l2_policy": f"inputs larger than L2: {msg >> 20} MiB messages rotating over {nslots} buffers",
                        "timing": "CUDA events on the posting stream, max over ranks"},
             "roofline": {"bound_gbps_per_gpu": round(R.copy_roofline_gbps(peaks), 1),
@@ -206,7 +212,7 @@ def main():
             "e2e": {"value": round(e2e_value, 2), "unit": "GB/s", "h2d_bytes_per_step": msg, "d2h_bytes_per_step": 64,
                     "h2d_only_gbps": round(h2d_gbps, 1), "cpu_affinity": f"{len(cpus)} cpus local to the GPU" if cpus else "unbound",
                     "path": "pinned host -> cudaMemcpyAsync H2D -> GPU-posted RDMA write -> status words in mapped pinned memory"},
-            "gpu_launches": args.steps, "gpu_launches_note": "one poster kernel per step, alternating over two QPs/streams; the DMA engine is one persistent kernel launched before the timed region",
+            "gpu_launches": args.steps, "gpu_launches_note": f"one poster kernel (one WQE) per step, {depth} steps in flight over {depth} QPs/streams; the DMA engine is one persistent kernel launched before the timed region",
             "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"), "reasons": clocks.get("reasons", []),
                        "samples": clocks.get("samples", 0)},
             "verified": ok, "extras": extras,

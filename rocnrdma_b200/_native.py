@@ -38,9 +38,8 @@ class RnQpCounters(C.Structure):
 
 
 class RnEngineStats(C.Structure):
-    _fields_ = [("n_polls", u64), ("n_chunks", u64), ("n_bulk_chunks", u64), ("dbg_last_db", u64),
-                ("dbg_t_start", u64), ("dbg_t_exit", u64), ("dbg_last_state", u64), ("running_ctas", u32),
-                ("exited_idle", u32), ("n_qps", u32), ("ctas", u32)]
+    _fields_ = [("n_bulk_chunks", u64), ("t_start", u64), ("t_exit", u64), ("running_ctas", u32),
+                ("exited_idle", u32), ("fatal", u32), ("n_qps", u32), ("ctas", u32), ("pad", u32)]
 
 
 _SIGS = {
@@ -89,6 +88,7 @@ _SIGS = {
     "rn_hca_set_remote_mkey": (i32, [vp, u64, u32, u64, u64, u64, u32, u32]),
     "rn_hca_work_stream": (u64, [vp]),
     "rn_hca_aux_stream": (u64, [vp]),
+    "rn_hca_stream": (u64, [vp, i32]),
     "rn_hca_dev_scratch": (u64, [vp, C.POINTER(u64)]),
     "rn_pack_record_bytes": (u64, [u64]),
     "rn_pack_tile_elems": (u32, []),

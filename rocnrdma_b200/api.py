@@ -216,6 +216,25 @@ class Context:
             self._aux = torch.cuda.ExternalStream(self._lib.rn_hca_aux_stream(self._h), device=self.device)
         return self._aux
 
+    def streams(self, n: int):
+        """The first ``n`` (<= 8) of the HCA's pre-created non-blocking streams (0 = ``stream``, 1 = ``aux_stream``)."""
+        import torch
+        if not 1 <= n <= 8:
+            raise ValueError("1..8 streams are pre-created per context")
+        if not hasattr(self, "_pool"):
+            self._pool = {}
+        out = []
+        for i in range(n):
+            if i == 0:
+                out.append(self.stream)
+            elif i == 1:
+                out.append(self.aux_stream)
+            else:
+                if i not in self._pool:
+                    self._pool[i] = torch.cuda.ExternalStream(self._lib.rn_hca_stream(self._h, i), device=self.device)
+                out.append(self._pool[i])
+        return out
+
     def dev_scratch(self, nbytes: int, offset: int = 0) -> int:
         """Address inside the HCA's zero-initialised device scratch (kernel counters; every
         kernel that uses it leaves it zeroed again)."""

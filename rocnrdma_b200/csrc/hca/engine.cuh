@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(kThreads, 1) engine_kernel(EngineCtl* ctl) {
     quit = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     atomicAdd(&ctl->running_ctas, 1u);
-    if (blockIdx.x == 0) ctl->dbg_t_start = globaltimer_ns();
+    if (blockIdx.x == 0) ctl->t_start = globaltimer_ns();
   }
   __syncthreads();
   unsigned long long last_activity = globaltimer_ns();
@@ -540,10 +540,6 @@ __global__ void __launch_bounds__(kThreads, 1) engine_kernel(EngineCtl* ctl) {
       s.have_work = 0;
       uint32_t n = ctl->n_qps;
       bool pending = false;
-      if (blockIdx.x == 0) {
-        ctl->n_polls = ctl->n_polls + 1;
-        if (n) { ctl->dbg_last_db = ld_u64_volatile(ctl->qps[0]->bf); ctl->dbg_last_state = ctl->qps[0]->state; }
-      }
       if (sticky_qp) {
         Resolved* sr = sticky_qp->resolved + (sticky_w & ((1u << sticky_qp->sq_log) - 1));
         // a successful draw is a claim that MUST be executed, whichever generation it names
@@ -621,7 +617,7 @@ __global__ void __launch_bounds__(kThreads, 1) engine_kernel(EngineCtl* ctl) {
     }
   }
   if (threadIdx.x == 0) {
-    if (blockIdx.x == 0) ctl->dbg_t_exit = globaltimer_ns();
+    if (blockIdx.x == 0) ctl->t_exit = globaltimer_ns();
     atomicSub(&ctl->running_ctas, 1u);
   }
 }

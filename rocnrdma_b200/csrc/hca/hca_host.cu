@@ -74,6 +74,7 @@ struct Qp {
 struct Hca {
   int dev = 0;
   cudaStream_t ctl = nullptr, eng = nullptr, work = nullptr, aux = nullptr;
+  cudaStream_t pool[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // extra pre-created poster streams
   uint8_t *arena = nullptr, *harena = nullptr;
   size_t arena_size = 0, arena_off = 0, harena_size = 0, harena_off = 0;
   uint32_t max_mkeys = 0;
@@ -183,6 +184,7 @@ RN_API int rn_hca_open(int dev, uint32_t max_mkeys, uint32_t max_qps, uint64_t a
   // is serialised behind a running persistent kernel by the driver.
   CU_OK(cudaStreamCreateWithFlags(&h->work, cudaStreamNonBlocking));
   CU_OK(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
+  for (auto& st : h->pool) CU_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   h->arena_size = arena_bytes ? arena_bytes : (64ull << 20);
   h->harena_size = host_arena_bytes ? host_arena_bytes : (16ull << 20);
   CU_OK(cudaMalloc(&h->arena, h->arena_size));
@@ -251,6 +253,14 @@ RN_API int rn_hca_enable_peer(void* hca, int peer_dev) {
 RN_API int rn_set_device(int dev) { return cudaSetDevice(dev) == cudaSuccess ? 0 : -19; }
 RN_API uint64_t rn_hca_work_stream(void* hca) { return (uint64_t)((Hca*)hca)->work; }
 RN_API uint64_t rn_hca_aux_stream(void* hca) { return (uint64_t)((Hca*)hca)->aux; }
+// stream i of the pre-created set: 0 = work, 1 = aux, 2..7 = pool
+RN_API uint64_t rn_hca_stream(void* hca, int i) {
+  Hca* h = (Hca*)hca;
+  if (i == 0) return (uint64_t)h->work;
+  if (i == 1) return (uint64_t)h->aux;
+  if (i >= 2 && i < 8) return (uint64_t)h->pool[i - 2];
+  return 0;
+}
 RN_API uint64_t rn_hca_scratch(void* hca, uint64_t* size) {
   Hca* h = (Hca*)hca;
   if (size) *size = h->scratch_size;
@@ -784,15 +794,14 @@ RN_API int rn_engine_stop(void* hca) {
   return 0;
 }
 
-struct RnEngineStats { uint64_t n_polls, n_chunks, n_bulk_chunks, dbg_last_db, dbg_t_start, dbg_t_exit, dbg_last_state; uint32_t running_ctas, exited_idle, n_qps, ctas; };
+struct RnEngineStats { uint64_t n_bulk_chunks, t_start, t_exit; uint32_t running_ctas, exited_idle, fatal, n_qps, ctas, pad; };
 RN_API int rn_engine_stats(void* hca, RnEngineStats* out) {
   Hca* h = (Hca*)hca;
   EngineCtl c;
   cudaSetDevice(h->dev);
   int rc = pull(h, &c, h->d_ctl, sizeof c);
   if (rc) return rc;
-  out->n_polls = c.n_polls; out->n_chunks = c.n_chunks; out->n_bulk_chunks = c.n_bulk_chunks;
-  out->dbg_last_db = c.dbg_last_db; out->dbg_t_start = c.dbg_t_start; out->dbg_t_exit = c.dbg_t_exit; out->dbg_last_state = c.dbg_last_state;
+  out->n_bulk_chunks = c.n_bulk_chunks; out->t_start = c.t_start; out->t_exit = c.t_exit; out->fatal = c.fatal; out->pad = 0;
   out->running_ctas = c.running_ctas; out->exited_idle = c.exited_idle; out->n_qps = c.n_qps;
   out->ctas = (uint32_t)h->engine_ctas;
   return 0;

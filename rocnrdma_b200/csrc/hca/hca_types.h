@@ -143,12 +143,11 @@ struct EngineCtl {
   unsigned int running_ctas;       // CTAs alive (atomic)
   unsigned int exited_idle;        // set when the watchdog ended the engine
   unsigned int fatal;              // a DMA never completed; engine bailed out
-  unsigned int hint;               // bumped when there is work for more CTAs than the doorbell watchers
-  unsigned int n_watchers;         // CTAs [0, n_watchers) poll doorbells; the rest sleep on `hint`
-  unsigned int quit_all;           // a watcher found the engine idle / drained: everybody leaves
+  unsigned int quit_all;           // the host-doorbell watcher found the engine idle / drained: everybody leaves
+  unsigned int pad;
   unsigned int oneshot;            // exit as soon as every queue is drained (profiling under ncu: kernels are serialised there)
-  unsigned long long n_polls, n_chunks, n_bulk_chunks;
-  unsigned long long dbg_last_db, dbg_t_start, dbg_t_exit, dbg_last_state;
+  unsigned long long n_bulk_chunks;     // chunks moved through the TMA bulk path
+  unsigned long long t_start, t_exit;   // %globaltimer of engine start / exit (CTA 0)
 };
 
 // Status codes returned by device-side waits (never spin forever: SURVEY.md section 5).
