@@ -137,10 +137,15 @@ RN_API int rn_k_shared_post_stress(uint64_t stream, uint64_t qp_dev, int ctas, u
 // ---------------------------------------------------------------- receive-side consumer
 // Waits on the QP's receive CQ for `n` arrivals (SEND or RDMA_WRITE_IMM), stamps each by its immediate.
 // out: [status, t_start, t_end, seen, bytes_total, 0,0,0] ; stamps[imm] = %globaltimer at observation.
+// With prepost_bytes != ~0 the kernel first posts its own `n` receive WQEs from the device (dev::post_recv):
+// buffer i is [prepost_addr + i * prepost_bytes, +prepost_bytes).
 __global__ void __launch_bounds__(32, 1) recv_consume_kernel(QpDev* qp, uint32_t n, uint32_t max_imm, unsigned long long* stamps,
-                                                             unsigned long long* out, unsigned long long timeout_ns) {
+                                                             unsigned long long* out, unsigned long long timeout_ns,
+                                                             uint64_t prepost_addr, uint32_t prepost_lkey, uint32_t prepost_bytes) {
   if (threadIdx.x != 0) return;
   const unsigned long long t0 = globaltimer_ns();
+  if (prepost_bytes != ~0u)
+    for (uint32_t i = 0; i < n; ++i) post_recv(qp, prepost_addr + (uint64_t)i * prepost_bytes, prepost_lkey, prepost_bytes);
   unsigned long long bytes = 0;
   uint32_t seen = 0;
   int status = WAIT_OK;
@@ -156,9 +161,11 @@ __global__ void __launch_bounds__(32, 1) recv_consume_kernel(QpDev* qp, uint32_t
   out[1] = t0; out[2] = globaltimer_ns(); out[3] = seen; out[4] = bytes;
 }
 RN_API int rn_k_recv_consume(uint64_t stream, uint64_t qp_dev, uint32_t n, uint32_t max_imm, uint64_t stamps_dev,
-                             uint64_t out_dev, uint64_t timeout_ms) {
+                             uint64_t out_dev, uint64_t timeout_ms, uint64_t prepost_addr, uint32_t prepost_lkey,
+                             uint32_t prepost_bytes) {
   recv_consume_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((QpDev*)qp_dev, n, max_imm, (unsigned long long*)stamps_dev,
-                                                          (unsigned long long*)out_dev, (timeout_ms ? timeout_ms : 2000) * 1000000ull);
+                                                          (unsigned long long*)out_dev, (timeout_ms ? timeout_ms : 2000) * 1000000ull,
+                                                          prepost_addr, prepost_lkey, prepost_bytes);
   return (int)cudaGetLastError();
 }
 

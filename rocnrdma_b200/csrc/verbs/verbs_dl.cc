@@ -42,6 +42,8 @@ RN_API int rn_verbs_compiled() { return 0; }
 
 #else  // ------------------------------------------------------------------ full backend
 
+#include <cuda_runtime.h>
+#include <errno.h>
 #include <infiniband/mlx5dv.h>
 #include <infiniband/verbs.h>
 
@@ -266,6 +268,42 @@ RN_API int rn_verbs_raw_qp(void* qp, RnRawQp* out) {
   out->qpn = q->qp->qp_num; out->cqn = dc.cqn;
   return 0;
 }
+// N3 on real hardware: make the NIC's queues visible to the GPU so hca/post.cuh can drive it.
+//   * SQ buffer and doorbell record are host memory owned by rdma-core: cudaHostRegister(Mapped) gives the
+//     GPU a device pointer to the same bytes (the NIC keeps reading them where it always did);
+//   * the BlueFlame / doorbell register is a PCIe BAR page of the HCA: cudaHostRegisterIoMemory maps it so an
+//     SM's 8-byte store becomes the MMIO doorbell write (needs the driver's PeerMappingOverride / IoMemory
+//     support; SURVEY.md section 7.4 item 2 -- the fallback is a CPU proxy ringing it);
+//   * the CQ buffer is registered the same way for the device-side poller.
+// The caller (hca_host.cu) wraps these pointers in a QpDev/CqDev so write_rdma_wqe / sq_submit / cq_poll_once
+// run unchanged: the wire format, the doorbell-record layout ([0] receive, [1] send) and the CQE owner-bit
+// rule are the ones this project already uses.
+struct RnGpuQp { uint64_t sq_dev, dbrec_dev, bf_dev, cq_dev, cq_dbrec_dev; uint32_t sq_wqe_cnt, cq_cqe_cnt, qpn, cqn; };
+RN_API int rn_verbs_map_qp_to_gpu(void* qp, RnGpuQp* out) {
+  RnRawQp raw;
+  int rc = rn_verbs_raw_qp(qp, &raw);
+  if (rc) return rc;
+  if (raw.sq_stride != 64 || raw.cq_cqe_size != 64) { snprintf(g_why, sizeof g_why, "unexpected WQE/CQE stride %u/%u", raw.sq_stride, raw.cq_cqe_size); return -22; }
+  auto map = [&](uint64_t host, size_t bytes, unsigned flags, uint64_t* dev) -> int {
+    uint64_t page = host & ~4095ull;
+    size_t len = ((host + bytes + 4095) & ~4095ull) - page;
+    cudaError_t e = cudaHostRegister((void*)page, len, flags);
+    if (e != cudaSuccess && e != cudaErrorHostMemoryAlreadyRegistered) { snprintf(g_why, sizeof g_why, "cudaHostRegister(0x%llx): %s", (unsigned long long)page, cudaGetErrorString(e)); cudaGetLastError(); return -5; }
+    cudaGetLastError();
+    void* d = nullptr;
+    if (cudaHostGetDevicePointer(&d, (void*)page, 0) != cudaSuccess) return -5;
+    *dev = (uint64_t)d + (host - page);
+    return 0;
+  };
+  if ((rc = map(raw.sq_buf, (size_t)raw.sq_wqe_cnt * 64, cudaHostRegisterMapped | cudaHostRegisterPortable, &out->sq_dev))) return rc;
+  if ((rc = map(raw.dbrec, 8, cudaHostRegisterMapped | cudaHostRegisterPortable, &out->dbrec_dev))) return rc;
+  if ((rc = map(raw.cq_buf, (size_t)raw.cq_cqe_cnt * 64, cudaHostRegisterMapped | cudaHostRegisterPortable, &out->cq_dev))) return rc;
+  if ((rc = map(raw.cq_dbrec, 8, cudaHostRegisterMapped | cudaHostRegisterPortable, &out->cq_dbrec_dev))) return rc;
+  if ((rc = map(raw.bf_reg, raw.bf_size ? raw.bf_size : 256, cudaHostRegisterIoMemory | cudaHostRegisterMapped | cudaHostRegisterPortable, &out->bf_dev))) return rc;
+  out->sq_wqe_cnt = raw.sq_wqe_cnt; out->cq_cqe_cnt = raw.cq_cqe_cnt; out->qpn = raw.qpn; out->cqn = raw.cqn;
+  return 0;
+}
+
 RN_API int rn_verbs_destroy_qp(void* qp) {
   QpH* q = (QpH*)qp;
   api().destroy_qp(q->qp);

@@ -120,14 +120,17 @@ def l2_flush(scratch: torch.Tensor, value: int = 0, stream=None):
 
 
 def recv_consume(qp, n: int, max_imm: int = 0, stamps=None, timeout_ms: int = 2000, stream=None, sync: bool = True,
-                 scratch_off: int = 8192):
+                 scratch_off: int = 8192, prepost_mr=None, prepost_bytes: int = 0):
     """Receive-side consumer kernel on ``qp``'s GPU: waits for ``n`` arrivals (SEND / RDMA_WRITE_IMM) on the
     receive CQ and, if ``stamps`` (int64 tensor on that GPU) is given, stamps %globaltimer per immediate."""
     ctx = qp.ctx
     ws = work_stream(ctx, stream)
     out_addr, out_view = ctx.scratch(64, offset=scratch_off)
+    # prepost_mr: the kernel posts its own n receive WQEs from the device before polling (buffer i at offset i * prepost_bytes)
     rc = N.load().rn_k_recv_consume(_stream_ptr(ws), qp.dev_ptr, n, max_imm, stamps.data_ptr() if stamps is not None else 0,
-                                    out_addr, timeout_ms)
+                                    out_addr, timeout_ms, prepost_mr.addr if prepost_mr is not None else 0,
+                                    prepost_mr.lkey if prepost_mr is not None else 0,
+                                    prepost_bytes if prepost_mr is not None else 0xFFFFFFFF)
     if rc:
         raise N.NativeError(f"recv_consume launch failed ({rc})")
     if not sync:

@@ -222,3 +222,26 @@ def test_gpu_posted_send_lands_in_posted_receive_buffers(ctx):
     assert all(w.opcode == W.CQE_RESP_SEND and w.byte_cnt == n for w in wcs)
     assert [w.wqe_counter for w in wcs] == list(range(k))          # receives are consumed in order
     assert torch.equal(src, dst)
+
+
+def test_device_preposted_receives_and_gpu_posted_sends(ctx):
+    """Both ends on the device: a consumer kernel posts its own receive WQEs (dev::post_recv) and polls the
+    receive CQ while a poster kernel SENDs; no host-posted work request anywhere."""
+    n, k = 8192, 6
+    src, dst = _bufs(n * k)
+    ms, md = ctx.reg_mr(src), ctx.reg_mr(dst)
+    cq_a, cq_b = ctx.create_cq(64), ctx.create_cq(64)
+    qa = ctx.create_qp(cq_a, cq_a, 16, 16)
+    qb = ctx.create_qp(cq_b, cq_b, 16, 16)
+    qa.connect(qb)
+    torch.cuda.synchronize()
+    ctx.engine_start(ctas=4, idle_timeout_ms=3000, rnr_timeout_ms=2000)
+    try:
+        view, rs = ops.recv_consume(qb, k, timeout_ms=3000, sync=False, stream=ctx.aux_stream, prepost_mr=md, prepost_bytes=n)
+        r = ops.rdma_stream(qa, W.OP_SEND, ms, None, n, iters=k, window=2, slot_stride=n, nslots=k)
+        rs.synchronize()
+    finally:
+        ctx.engine_stop()
+    cons = ops.parse_recv(view)
+    assert r.ok and cons["status"] == "OK" and cons["seen"] == k and cons["bytes"] == n * k, (r, cons)
+    assert torch.equal(src, dst)
