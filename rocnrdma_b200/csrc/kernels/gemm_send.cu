@@ -341,6 +341,248 @@ gemm_send_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 }
 
+// ==================================================================== cta_group::2 variant
+// Two CTAs of one cluster (a TPC pair) compute one 256x256 tile: each owns 128 rows of A and of the
+// accumulator (its own TMEM) and loads only HALF of the B tile; the 5th-gen tensor core of each SM
+// reads the other half from its partner's shared memory.  Per 256x256x64 step a pair moves
+// 2 x (16 + 16) KiB instead of 2 x (16 + 32) KiB through L2 -- the 1-CTA kernel already sat at 48 % L2
+// throughput at 4096^3 and lost 21 % to cuBLAS at 8192^3 -- and the 32 KiB stages allow a 6-deep ring.
+//   * TMA loads carry .cta_group::2 and complete on the LEADER's full barrier (both CTAs' bytes; only the
+//     leader arrives on it, the partner's loads just deliver their transaction bytes);
+//   * only the leader's MMA thread issues tcgen05.mma.cta_group::2 (M = 256);
+//   * tcgen05.commit multicasts to the same barrier in both CTAs (stage release, accumulator ready);
+//   * the partner's epilogue warps hand TMEM back with a remote mbarrier arrive on the leader.
+constexpr int STAGES2 = 6;
+constexpr int BH_STAGE = (BN / 2) * BK * 2;     // half of the B tile: 16 KiB
+struct alignas(1024) Smem2 {
+  uint8_t a[STAGES2][A_STAGE];
+  uint8_t b[STAGES2][BH_STAGE];
+  alignas(8) uint64_t full[STAGES2], empty[STAGES2], tfull[2], tempty[2];
+  uint32_t tmem_base;
+  volatile int abort;
+};
+constexpr uint32_t kIdesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a shared::cta address in this CTA) as seen in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t cta_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(s32(smem_dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(s32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+template <typename S>
+__device__ __forceinline__ bool mbar_wait_t(S& s, uint64_t* b, uint32_t parity) {
+  if (mbar_try(b, parity)) return true;
+  unsigned long long t0 = globaltimer_ns();
+  unsigned n = 0;
+  while (!mbar_try(b, parity)) {
+    if ((++n & 255) == 0) {
+      if (s.abort) return false;
+      if (globaltimer_ns() - t0 > kWaitNs) { s.abort = 1; return false; }
+    }
+  }
+  return true;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_send2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  Smem2& s = *reinterpret_cast<Smem2*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();
+  const bool leader = rank == 0;
+  const unsigned long long t_start = globaltimer_ns();
+  const uint32_t mp_blks = g.M / (2 * BM), n_blks = g.N / BN, k_blks = g.K / BK;
+  const uint32_t n_tiles = mp_blks * n_blks, n_clusters = gridDim.x / 2, cluster_id = blockIdx.x / 2;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES2; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s.tfull[i], 1); mbar_init(&s.tempty[i], 8); }
+    s.abort = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+  }
+  if (warp == 1) {   // same warp id in both CTAs, whole warp
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&s.tmem_base)), "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                 // partner's barriers exist before anything is multicast to them
+  tc_fence_after();
+  const uint32_t tmem_base = s.tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs: own A rows, own half of B)
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (uint32_t tile = cluster_id; tile < n_tiles && !s.abort; tile += n_clusters) {
+        const uint32_t mp = tile / n_blks, n_blk = tile % n_blks;
+        for (uint32_t kb = 0; kb < k_blks; ++kb) {
+          if (!mbar_wait_t(s, &s.empty[stage], phase ^ 1)) goto producer2_done;
+          const uint32_t lbar = mapa(s32(&s.full[stage]), 0);
+          // Only the leader arrives (expecting BOTH CTAs' bytes); the partner's TMA completes its bytes on
+          // the leader's barrier by itself.  A remote release-arrive from the partner here cost a
+          // cluster-scope memory barrier per k-block and halved the kernel (ncu: tensor pipe 35 %).
+          if (leader) mbar_expect_tx(&s.full[stage], 2 * (A_STAGE + BH_STAGE));
+          tma_load_2d_2sm(s.a[stage], &tmap_a, lbar, (int)(kb * BK), (int)(mp * 2 * BM + rank * BM));
+          tma_load_2d_2sm(s.b[stage], &tmap_b, lbar, (int)(kb * BK), (int)(n_blk * BN + rank * (BN / 2)));
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  producer2_done:
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only)
+    if (leader && lane == 0) {
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (uint32_t tile = cluster_id; tile < n_tiles && !s.abort; tile += n_clusters) {
+        if (!mbar_wait_t(s, &s.tempty[acc], acc_phase ^ 1)) goto mma2_done;   // both CTAs' epilogues drained this buffer
+        tc_fence_after();
+        const uint32_t d = tmem_base + acc * BN;
+        for (uint32_t kb = 0; kb < k_blks; ++kb) {
+          if (!mbar_wait_t(s, &s.full[stage], phase)) goto mma2_done;          // both CTAs' A and B halves landed
+          tc_fence_after();
+          const uint64_t da = smem_desc(s.a[stage]), db = smem_desc(s.b[stage]);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_f16_2sm(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc2, (kb | (uint32_t)k) != 0);
+          tc_commit_2sm(&s.empty[stage]);                                      // frees the stage in BOTH CTAs
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_2sm(&s.tfull[acc]);                                          // accumulators ready in BOTH CTAs
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  mma2_done:
+    __syncwarp();
+  } else {
+    // ===================== epilogue (both CTAs: their own 128 rows of the 256-row tile)
+    const uint32_t q = warp & 3;
+    uint32_t acc = 0, acc_phase = 0;
+    const bool sys = g.qp != nullptr && g.qp->sys_scope != 0;
+    for (uint32_t tile = cluster_id; tile < n_tiles; tile += n_clusters) {
+      const uint32_t mp = tile / n_blks, n_blk = tile % n_blks;
+      const uint32_t m_blk = mp * 2 + rank;                                    // 128-row panel index
+      if (!mbar_wait_t(s, &s.tfull[acc], acc_phase)) break;
+      tc_fence_after();
+      const uint32_t row_in_panel = q * 32 + lane;
+      const uint32_t row = m_blk * BM + row_in_panel;
+      const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * BN;
+      if (!g.out_fp8) {
+        __nv_bfloat16* crow = g.c + (size_t)row * g.N + (size_t)n_blk * BN;
+#pragma unroll 2
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          tmem_ld_wait();
+          uint4* dst = reinterpret_cast<uint4*>(crow + c * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            dst[j] = make_uint4(pack_bf16(r[8 * j], r[8 * j + 1]), pack_bf16(r[8 * j + 2], r[8 * j + 3]),
+                                pack_bf16(r[8 * j + 4], r[8 * j + 5]), pack_bf16(r[8 * j + 6], r[8 * j + 7]));
+        }
+      } else {
+        uint8_t* rec = reinterpret_cast<uint8_t*>(g.c) + (uint64_t)m_blk * panel_record_bytes(g.N);
+        uint8_t* qrow = rec + (size_t)row_in_panel * g.N + (size_t)n_blk * BN;
+        uint8_t* srow = rec + (size_t)BM * g.N + (size_t)row_in_panel * (g.N / 32) + (size_t)n_blk * (BN / 32);
+#pragma unroll 2
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          tmem_ld_wait();
+          quantize_block(r, reinterpret_cast<uint4*>(qrow + c * 32), srow + c);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {                                                         // 8 arrivals (4 warps x 2 CTAs) on the LEADER's barrier
+        if (leader) mbar_arrive(&s.tempty[acc]);
+        else mbar_arrive_remote(mapa(s32(&s.tempty[acc]), 0));
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (g.qp != nullptr) {
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        if (threadIdx.x == 64) {
+          fence_gpu();
+          unsigned int old = atomicAdd(&g.counters[m_blk], 1u);
+          if (old + 1 == n_blks) {
+            fence_scope(sys);
+            const uint64_t panel_bytes = g.out_fp8 ? panel_record_bytes(g.N) : (uint64_t)BM * g.N * 2, off = (uint64_t)m_blk * panel_bytes;
+            unsigned long long idx = sq_reserve(g.qp, 1, g.timeout_ns);
+            const bool sig = g.signal_every <= 1 || ((idx + 1) % g.signal_every == 0);
+            if (idx != ~0ull) {
+              write_rdma_wqe(g.qp, idx, g.with_imm ? OP_RDMA_WRITE_IMM : OP_RDMA_WRITE, g.c_va + off, g.lkey, g.remote_va + off, g.rkey,
+                             (uint32_t)panel_bytes, sig ? CTRL_CQ_UPDATE : 0, m_blk);
+              sq_submit(g.qp, idx, 1, g.timeout_ns, true);
+              atomicMax(&g.acc[0], idx + 1);
+              atomicAdd(&g.acc[1], 1ull);
+              atomicMax(&g.acc[2], ~globaltimer_ns());
+            } else g.out[0] = (unsigned long long)(long long)WAIT_TIMEOUT;
+            g.counters[m_blk] = 0;
+          }
+        }
+      }
+    }
+  }
+
+  // ===================== teardown
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                 // nobody frees TMEM while the partner's tensor core may still write it
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+  }
+  if (threadIdx.x == 64) {
+    if (s.abort) g.out[0] = (unsigned long long)(long long)WAIT_TIMEOUT;
+    fence_gpu();
+    unsigned int old = atomicAdd(&g.counters[g.M / BM], 1u);
+    if (old + 1 == gridDim.x) {
+      const unsigned long long t_compute_end = globaltimer_ns();
+      fence_gpu();
+      unsigned long long posted = ld_u64_volatile(&g.acc[1]);
+      if (g.qp != nullptr) {
+        int rc = WAIT_TIMEOUT;
+        unsigned long long fidx = sq_reserve(g.qp, 1, g.timeout_ns);
+        if (fidx != ~0ull) {
+          uint8_t* slot = g.qp->sq + ((fidx & ((1ull << g.qp->sq_log) - 1)) << 6);
+          st_v4(slot + 0, ctrl_word0(OP_NOP, (uint16_t)fidx), ctrl_word1(g.qp->qpn, 1), (uint32_t)CTRL_CQ_UPDATE << 24, 0u);
+          st_v4(slot + 16, 0u, 0u, 0u, 0u); st_v4(slot + 32, 0u, 0u, 0u, 0u); st_v4(slot + 48, 0u, 0u, 0u, 0u);
+          if (sq_submit(g.qp, fidx, 1, g.timeout_ns, true) == WAIT_OK) rc = sq_wait(g.qp, fidx, g.timeout_ns);
+        }
+        if (posted != g.M / BM && rc == WAIT_OK) rc = WAIT_TIMEOUT;
+        if (rc != WAIT_OK) g.out[0] = (unsigned long long)(long long)rc;
+      }
+      g.out[1] = t_start; g.out[2] = globaltimer_ns(); g.out[3] = posted;
+      g.out[4] = ~ld_u64_volatile(&g.acc[2]); g.out[5] = t_compute_end; g.out[6] = 2;   // [6] = cta_group used
+      g.counters[g.M / BM] = 0;
+      g.acc[0] = 0; g.acc[1] = 0; g.acc[2] = 0;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ host: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -377,7 +619,8 @@ RN_API uint32_t rn_gemm_tile(uint32_t* bm, uint32_t* bn, uint32_t* bk) { *bm = B
 // counters_dev: >= (M/128 + 1) * 4 + 32 bytes of zeroed device scratch (self-cleaning), out_dev: 64 B mapped pinned.
 RN_API int rn_k_gemm_send(uint64_t stream, int grid, uint64_t a, uint64_t b, uint64_t c, uint32_t M, uint32_t N, uint32_t K,
                           uint64_t qp_dev, uint64_t c_va, uint32_t lkey, uint64_t remote_va, uint32_t rkey,
-                          uint32_t signal_every, uint32_t with_imm, uint32_t out_fp8, uint64_t counters_dev, uint64_t out_dev, uint64_t timeout_ms) {
+                          uint32_t signal_every, uint32_t with_imm, uint32_t out_fp8, uint32_t cta_group, uint64_t counters_dev, uint64_t out_dev,
+                          uint64_t timeout_ms) {
   if (!M || !N || !K || M % BM || N % BN || K % BK) return -22;
   if ((a | b | c) & 15) return -22;
   CUtensorMap ma, mb;
@@ -394,16 +637,26 @@ RN_API int rn_k_gemm_send(uint64_t stream, int grid, uint64_t a, uint64_t b, uin
   g.timeout_ns = (timeout_ms ? timeout_ms : 2000) * 1000000ull;
   unsigned long long* o = (unsigned long long*)out_dev;
   for (int i = 0; i < 8; ++i) o[i] = 0;
-  const uint32_t n_tiles = m_blks * (N / BN);
   if (grid <= 0) grid = 148;
+  const bool two = cta_group != 1 && (M % (2 * BM)) == 0 && grid >= 2;
+  if (two) {
+    // pairs of CTAs share a 256x256 tile: B map delivers half tiles (128 rows)
+    rc = make_map(&mb, (const void*)b, N, K, BN / 2);
+    if (rc) return rc;
+    const uint32_t n_tiles = (M / (2 * BM)) * (N / BN);
+    grid &= ~1;
+    if ((uint32_t)grid > 2 * n_tiles) grid = (int)(2 * n_tiles);
+    const size_t smem = sizeof(Smem2) + 1024;
+    cudaError_t e = cudaFuncSetAttribute(gemm_send2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return -(int)e - 1000;
+    gemm_send2_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ma, mb, g);
+    return (int)cudaGetLastError();
+  }
+  const uint32_t n_tiles = m_blks * (N / BN);
   if ((uint32_t)grid > n_tiles) grid = (int)n_tiles;
   const size_t smem = sizeof(Smem) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_send_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return -(int)e - 1000;
-    attr_set = true;
-  }
+  cudaError_t e = cudaFuncSetAttribute(gemm_send_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return -(int)e - 1000;
   gemm_send_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ma, mb, g);
   return (int)cudaGetLastError();
 }
@@ -412,5 +665,7 @@ extern "C" __attribute__((visibility("default"))) void rn_preload_gemm() {
   cudaFuncAttributes at;
   cudaFuncGetAttributes(&at, gemm_send_kernel);
   cudaFuncSetAttribute(gemm_send_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Smem) + 1024));
+  cudaFuncGetAttributes(&at, gemm_send2_kernel);
+  cudaFuncSetAttribute(gemm_send2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Smem2) + 1024));
   encode_tiled();
 }

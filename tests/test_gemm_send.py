@@ -101,3 +101,46 @@ def test_gemm_fp8_epilogue_records_match_reference_and_arrive(ctx):
     got = ops.dequant_fp8_panels(d, M, N)
     blk = ref32.reshape(M, N // 32, 32).abs().amax(dim=2, keepdim=True).expand(-1, -1, 32).reshape(M, N)
     assert torch.all((got - ref32).abs() <= blk * (2.0 ** -4) * 1.05 + 1e-2)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (256, 512, 512), (1024, 1024, 2048), (512, 768, 192)])
+def test_gemm_cta_pair_kernel_matches_fp32_reference(ctx, M, N, K):
+    torch.manual_seed(M * 3 + N + K)
+    a = torch.randn(M, K, device="cuda:0").to(torch.bfloat16)
+    b = torch.randn(N, K, device="cuda:0").to(torch.bfloat16)
+    c = torch.zeros(M, N, device="cuda:0", dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+    r = ops.gemm_send(ctx, a, b, c, cta_group=2)
+    assert r.ok, r.status
+    _check(c, _ref(a, b), K)
+
+
+def test_gemm_cta_pair_identity_layout(ctx):
+    M, N, K = 512, 512, 512
+    a = torch.eye(M, K, device="cuda:0").to(torch.bfloat16)
+    b = (torch.arange(N * K, device="cuda:0").reshape(N, K) % 251).to(torch.bfloat16)
+    c = torch.zeros(M, N, device="cuda:0", dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+    r = ops.gemm_send(ctx, a, b, c, cta_group=2)
+    assert r.ok
+    assert torch.equal(c, b.T[:M].contiguous())
+
+
+def test_gemm_cta_pair_send_panels(ctx):
+    M, N, K = 1024, 1024, 1024
+    torch.manual_seed(5)
+    a = torch.randn(M, K, device="cuda:0").to(torch.bfloat16)
+    b = torch.randn(N, K, device="cuda:0").to(torch.bfloat16)
+    c = torch.zeros(M, N, device="cuda:0", dtype=torch.bfloat16)
+    d = torch.zeros_like(c)
+    cm, dm = ctx.reg_mr(c), ctx.reg_mr(d)
+    qp = ctx.loopback_qp(depth=64)
+    torch.cuda.synchronize()
+    ctx.engine_start(ctas=16, idle_timeout_ms=3000)
+    try:
+        r = ops.gemm_send(ctx, a, b, c, c_mr=cm, qp=qp, dst_mr=dm, signal_every=4, cta_group=2, grid=64)
+    finally:
+        ctx.engine_stop()
+    assert r.ok and r.panels_posted == M // 128, r
+    _check(c, _ref(a, b), K)
+    assert torch.equal(c, d)

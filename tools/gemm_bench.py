@@ -25,9 +25,12 @@ for (M, N, K) in shapes:
         for _ in range(10): torch.matmul(a, b.T, out=c)
         ev[1].record(); ev[1].synchronize()
     cublas_tf = flops * 10 / (ev[0].elapsed_time(ev[1]) * 1e-3) / 1e12
-    for _ in range(2): r = ops.gemm_send(ctx, a, b, c)
-    best = max(ops.gemm_send(ctx, a, b, c).tflops for _ in range(5))
-    row = dict(M=M, N=N, K=K, cublas_tflops=round(cublas_tf, 1), ours_tflops=round(best, 1), frac_of_cublas=round(best / cublas_tf, 3))
+    for _ in range(2): r = ops.gemm_send(ctx, a, b, c, cta_group=1)
+    best = max(ops.gemm_send(ctx, a, b, c, cta_group=1).tflops for _ in range(5))
+    for _ in range(2): ops.gemm_send(ctx, a, b, c, cta_group=2)
+    best2 = max(ops.gemm_send(ctx, a, b, c, cta_group=2).tflops for _ in range(5))
+    row = dict(M=M, N=N, K=K, cublas_tflops=round(cublas_tf, 1), ours_1cta_tflops=round(best, 1), frac_1cta=round(best / cublas_tf, 3),
+               ours_2cta_tflops=round(best2, 1), frac_2cta=round(best2 / cublas_tf, 3))
     for ectas in [16]:
         ctx.engine_start(ctas=ectas, idle_timeout_ms=3000)
         grid = 148 - ectas

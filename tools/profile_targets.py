@@ -15,14 +15,14 @@ from rocnrdma_b200.ops import pack as P
 
 what = sys.argv[1]
 ctx = rn.Context(0)
-if what == "gemm":
+if what in ("gemm", "gemm2"):
     M = N = K = 4096
     a = torch.randn(M, K, device="cuda").to(torch.bfloat16); b = torch.randn(N, K, device="cuda").to(torch.bfloat16)
     c = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
     torch.cuda.synchronize()
     for _ in range(3):
-        r = ops.gemm_send(ctx, a, b, c)
-    print("gemm", r.ok, round(r.tflops, 1), "TFLOP/s")
+        r = ops.gemm_send(ctx, a, b, c, cta_group=2 if what == "gemm2" else 1)
+    print(what, r.ok, round(r.tflops, 1), "TFLOP/s")
 elif what == "pack":
     n = 1 << 28
     x = torch.empty(n, dtype=torch.bfloat16, device="cuda"); ops.fill_bf16(x, 1, 1.0)
