@@ -136,8 +136,15 @@ __device__ __forceinline__ void ring_doorbell(QpDev* qp, unsigned long long to, 
 }
 
 // Single-poster submit: the calling thread is the only one posting to this QP.
+// Scope of the POSTER's fences: system scope only when the send queue / doorbell are outside this GPU
+// (host-resident rings, a real NIC).  A device-resident queue is consumed by the engine on the same
+// GPU, so gpu scope is enough even if the responder is another GPU -- publishing remotely-visible
+// bytes is the engine's job (QpDev::sys_scope).  (Using system scope here stretched a 230 us GEMM to
+// 470 us when its panels went over NVLink: each MEMBAR.SYS stalled an epilogue.)
+__device__ __forceinline__ bool poster_sys(const QpDev* qp) { return qp->sq_in_device == 0; }
+
 __device__ __forceinline__ int sq_submit_exclusive(QpDev* qp, unsigned long long idx, uint32_t n) {
-  const bool sys = qp->sys_scope != 0;
+  const bool sys = poster_sys(qp);
   ring_doorbell(qp, idx + n, sys);
   trace_stamp(qp, idx, TR_POST);
   st_u64_relaxed(&qp->ready_head, idx + n);
@@ -155,7 +162,7 @@ __device__ __forceinline__ int sq_submit_exclusive(QpDev* qp, unsigned long long
 // The flag store / lock and unlock / flag load pairs form a store-buffering pattern, hence the
 // sequentially-consistent fences (__threadfence*), not acq_rel ones.
 __device__ __forceinline__ int sq_submit_shared(QpDev* qp, unsigned long long idx, uint32_t n) {
-  const bool sys = qp->sys_scope != 0;
+  const bool sys = poster_sys(qp);
   const unsigned long long mask = (1ull << qp->sq_log) - 1;
   if (sys) __threadfence_system(); else __threadfence();          // WQE bytes before the flag
   for (uint32_t i = 0; i < n; ++i) st_u32_volatile(&qp->ready_flags[(idx + i) & mask], (uint32_t)(idx + i + 1));

@@ -237,7 +237,7 @@ gemm_send_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ===================== epilogue (4 warps <-> 4 TMEM lane quarters)
     const uint32_t q = warp & 3;
     uint32_t acc = 0, acc_phase = 0;
-    const bool sys = g.qp != nullptr && g.qp->sys_scope != 0;
+    const bool sys = g.qp != nullptr && poster_sys(g.qp);
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const uint32_t m_blk = tile / n_blks, n_blk = tile % n_blks;
       if (!mbar_wait(s, &s.tfull[acc], acc_phase)) break;
@@ -481,7 +481,7 @@ gemm_send2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // ===================== epilogue (both CTAs: their own 128 rows of the 256-row tile)
     const uint32_t q = warp & 3;
     uint32_t acc = 0, acc_phase = 0;
-    const bool sys = g.qp != nullptr && g.qp->sys_scope != 0;
+    const bool sys = g.qp != nullptr && poster_sys(g.qp);
     for (uint32_t tile = cluster_id; tile < n_tiles; tile += n_clusters) {
       const uint32_t mp = tile / n_blks, n_blk = tile % n_blks;
       const uint32_t m_blk = mp * 2 + rank;                                    // 128-row panel index

@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(kPackThreads) pack_fp8_write_kernel(PackArgs a
   const uint32_t G = (tiles_per_chunk % 4 == 0) ? 4 : ((tiles_per_chunk % 2 == 0) ? 2 : 1);
   const uint64_t n_groups = n_tiles / G;
   const uint32_t groups_per_chunk = tiles_per_chunk / G;
-  const bool sys = a.qp != nullptr && a.qp->sys_scope != 0;
+  const bool sys = a.qp != nullptr && poster_sys(a.qp);
   __shared__ int posted_here;
   if (threadIdx.x == 0) posted_here = 0;
   for (uint64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {

@@ -30,7 +30,7 @@ class SendRecvResult:
     verified: bool
 
 
-def run(M: int = 8192, N: int = 8192, K: int = 2048, engine_ctas: int = 16, gpus=(0, 1), reps: int = 3) -> SendRecvResult:
+def run(M: int = 8192, N: int = 8192, K: int = 2048, engine_ctas: int = 32, gpus=(0, 1), reps: int = 3) -> SendRecvResult:
     g0, g1 = gpus
     d0, d1 = torch.device("cuda", g0), torch.device("cuda", g1)
     tx, rx = Context(g0), Context(g1)
