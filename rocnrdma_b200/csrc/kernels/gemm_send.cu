@@ -59,11 +59,26 @@ struct GemmArgs {
   uint32_t signal_every;
   uint32_t with_imm;         // 1: RDMA_WRITE_IMM, immediate = panel index (wakes a consumer on the receiving GPU)
   uint32_t out_fp8;          // 1: epilogue emits block-scaled fp8 panel records instead of bf16 rows (see below)
+  uint32_t group_m;          // tile rasterisation: this many M blocks advance together across N (L2 reuse of B)
   unsigned int* counters;    // [0..m_blks): tiles done per panel ; [m_blks]: CTAs done
   unsigned long long* acc;   // [0] max idx+1, [1] posted, [2] ~first post time
   unsigned long long* out;   // [status, t_start, t_end, posted, t_first_post, t_compute_end, 0, 0]
   uint64_t timeout_ns;
 };
+
+// Tile order.  Plain N-fastest order re-streams the whole B matrix once per M block; at 8192^3 that is
+// 4.3 GB of reads of a 134 MB operand that does not fit the 126 MB L2 -- most of the kernel's time.
+// Grouped order: `group_m` M blocks advance together across N (M fastest inside the group), so the
+// clusters running at the same time share B tiles in L2.  Panels of a group complete together, group
+// by group, which is still progressive for the sender.
+__device__ __forceinline__ void tile_coords(uint32_t t, uint32_t m_blks, uint32_t n_blks, uint32_t group_m, uint32_t* m, uint32_t* n) {
+  const uint32_t per_group = group_m * n_blks;
+  const uint32_t grp = t / per_group, r = t % per_group;
+  const uint32_t m0 = grp * group_m;
+  const uint32_t gm = min(group_m, m_blks - m0);
+  *m = m0 + r % gm;
+  *n = r / gm;
+}
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -197,7 +212,8 @@ gemm_send_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (uint32_t tile = blockIdx.x; tile < n_tiles && !s.abort; tile += gridDim.x) {
-        const uint32_t m_blk = tile / n_blks, n_blk = tile % n_blks;
+        uint32_t m_blk, n_blk;
+        tile_coords(tile, m_blks, n_blks, g.group_m, &m_blk, &n_blk);
         for (uint32_t kb = 0; kb < k_blks; ++kb) {
           if (!mbar_wait(s, &s.empty[stage], phase ^ 1)) goto producer_done;
           mbar_expect_tx(&s.full[stage], A_STAGE + B_STAGE);
@@ -239,7 +255,8 @@ gemm_send_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint32_t acc = 0, acc_phase = 0;
     const bool sys = g.qp != nullptr && poster_sys(g.qp);
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const uint32_t m_blk = tile / n_blks, n_blk = tile % n_blks;
+      uint32_t m_blk, n_blk;
+      tile_coords(tile, m_blks, n_blks, g.group_m, &m_blk, &n_blk);
       if (!mbar_wait(s, &s.tfull[acc], acc_phase)) break;
       tc_fence_after();
       const uint32_t row_in_panel = q * 32 + lane;
@@ -437,7 +454,8 @@ gemm_send2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (uint32_t tile = cluster_id; tile < n_tiles && !s.abort; tile += n_clusters) {
-        const uint32_t mp = tile / n_blks, n_blk = tile % n_blks;
+        uint32_t mp, n_blk;
+        tile_coords(tile, mp_blks, n_blks, g.group_m, &mp, &n_blk);
         for (uint32_t kb = 0; kb < k_blks; ++kb) {
           if (!mbar_wait_t(s, &s.empty[stage], phase ^ 1)) goto producer2_done;
           const uint32_t lbar = mapa(s32(&s.full[stage]), 0);
@@ -483,7 +501,8 @@ gemm_send2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     uint32_t acc = 0, acc_phase = 0;
     const bool sys = g.qp != nullptr && poster_sys(g.qp);
     for (uint32_t tile = cluster_id; tile < n_tiles; tile += n_clusters) {
-      const uint32_t mp = tile / n_blks, n_blk = tile % n_blks;
+      uint32_t mp, n_blk;
+      tile_coords(tile, mp_blks, n_blks, g.group_m, &mp, &n_blk);
       const uint32_t m_blk = mp * 2 + rank;                                    // 128-row panel index
       if (!mbar_wait_t(s, &s.tfull[acc], acc_phase)) break;
       tc_fence_after();
@@ -619,8 +638,8 @@ RN_API uint32_t rn_gemm_tile(uint32_t* bm, uint32_t* bn, uint32_t* bk) { *bm = B
 // counters_dev: >= (M/128 + 1) * 4 + 32 bytes of zeroed device scratch (self-cleaning), out_dev: 64 B mapped pinned.
 RN_API int rn_k_gemm_send(uint64_t stream, int grid, uint64_t a, uint64_t b, uint64_t c, uint32_t M, uint32_t N, uint32_t K,
                           uint64_t qp_dev, uint64_t c_va, uint32_t lkey, uint64_t remote_va, uint32_t rkey,
-                          uint32_t signal_every, uint32_t with_imm, uint32_t out_fp8, uint32_t cta_group, uint64_t counters_dev, uint64_t out_dev,
-                          uint64_t timeout_ms) {
+                          uint32_t signal_every, uint32_t with_imm, uint32_t out_fp8, uint32_t cta_group, uint32_t group_m, uint64_t counters_dev,
+                          uint64_t out_dev, uint64_t timeout_ms) {
   if (!M || !N || !K || M % BM || N % BN || K % BK) return -22;
   if ((a | b | c) & 15) return -22;
   CUtensorMap ma, mb;
@@ -629,7 +648,7 @@ RN_API int rn_k_gemm_send(uint64_t stream, int grid, uint64_t a, uint64_t b, uin
   if (rc) return rc;
   GemmArgs g;
   g.c = (__nv_bfloat16*)c; g.M = M; g.N = N; g.K = K; g.qp = (QpDev*)qp_dev; g.c_va = c_va; g.lkey = lkey; g.rkey = rkey;
-  g.remote_va = remote_va; g.signal_every = signal_every ? signal_every : 1; g.with_imm = with_imm; g.out_fp8 = out_fp8;
+  g.remote_va = remote_va; g.signal_every = signal_every ? signal_every : 1; g.with_imm = with_imm; g.out_fp8 = out_fp8; g.group_m = group_m ? group_m : 1;
   const uint32_t m_blks = M / BM;
   g.counters = (unsigned int*)counters_dev;
   g.acc = (unsigned long long*)(counters_dev + (((uint64_t)m_blks + 1) * 4 + 7) / 8 * 8);

@@ -69,13 +69,14 @@ def dequant_fp8_panels(rec: torch.Tensor, M: int, Nn: int) -> torch.Tensor:
 
 
 def gemm_send(ctx, a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, c_mr=None, qp=None, dst_mr=None,
-              signal_every: int = 1, with_imm: bool = False, out_fp8: bool = False, cta_group: int = 0, grid: int = 0, timeout_ms: int = 2000, stream=None, sync: bool = True,
+              signal_every: int = 1, with_imm: bool = False, out_fp8: bool = False, cta_group: int = 0, group_m: int = 0, grid: int = 0, timeout_ms: int = 2000, stream=None, sync: bool = True,
               scratch_slot: int = 2):
     """``c[M,N] = a[M,K] @ b[N,K].T`` (bf16 in/out, fp32 accumulate on the 5th-gen tensor cores).
 
     With ``qp``/``c_mr``/``dst_mr`` every finished 128-row panel of ``c`` is RDMA-written to the same
     offset of ``dst_mr`` from inside the kernel; the call returns when the last panel has landed.
     Shapes must be multiples of the tile: M % 128 == 0, N % 256 == 0, K % 64 == 0.
+    ``group_m``: M blocks that advance together across N (L2 reuse of B; 0 = 8 for compute only, 4 when sending).
     ``cta_group``: 2 = CTA-pair kernel (256x256 tiles, the B operand shared across the pair; measured
     1.05-1.11x cuBLAS at 4096^3 .. 16384x4096x1024), 1 = single-CTA 128x256 kernel, 0 (default) = the pair
     kernel whenever M % 256 == 0.
@@ -96,6 +97,10 @@ def gemm_send(ctx, a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, c_mr=None,
         raise ValueError("sending needs c_mr (registration of c) and dst_mr")
     if cta_group == 0:
         cta_group = 2 if M % (2 * BM) == 0 else 1
+    if group_m == 0:
+        # tile rasterisation: M blocks (pairs for cta_group 2) that advance together across N; more = better
+        # L2 reuse of B, fewer = panels complete (and are sent) more evenly
+        group_m = 8 if qp is None else 4
     lib = N.load()
     ws = work_stream(ctx, stream)
     m_blks = M // BM
@@ -104,7 +109,7 @@ def gemm_send(ctx, a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, c_mr=None,
     rc = lib.rn_k_gemm_send(_stream_ptr(ws), grid, a.data_ptr(), b.data_ptr(), c.data_ptr(), M, Nn, K,
                             qp.dev_ptr if qp is not None else 0, c_mr.addr if c_mr is not None else 0,
                             c_mr.lkey if c_mr is not None else 0, dst_mr.addr if dst_mr is not None else 0,
-                            dst_mr.rkey if dst_mr is not None else 0, signal_every, int(with_imm), int(out_fp8), cta_group, counters, out_addr, timeout_ms)
+                            dst_mr.rkey if dst_mr is not None else 0, signal_every, int(with_imm), int(out_fp8), cta_group, group_m, counters, out_addr, timeout_ms)
     if rc:
         raise N.NativeError(f"gemm_send launch failed ({rc})")
     if not sync:

@@ -144,3 +144,17 @@ def test_gemm_cta_pair_send_panels(ctx):
     assert r.ok and r.panels_posted == M // 128, r
     _check(c, _ref(a, b), K)
     assert torch.equal(c, d)
+
+
+@pytest.mark.parametrize("cta_group,group_m", [(1, 1), (1, 3), (2, 1), (2, 3), (2, 16)])
+def test_gemm_tile_rasterisation_orders(ctx, cta_group, group_m):
+    """Grouped tile orders (incl. a group size that does not divide the M blocks) cover every tile exactly once."""
+    M, N, K = 1280, 768, 128           # 10 M blocks / 5 pairs: ragged last group for group_m = 3
+    torch.manual_seed(group_m)
+    a = torch.randn(M, K, device="cuda:0").to(torch.bfloat16)
+    b = torch.randn(N, K, device="cuda:0").to(torch.bfloat16)
+    c = torch.full((M, N), float("nan"), device="cuda:0", dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+    r = ops.gemm_send(ctx, a, b, c, cta_group=cta_group, group_m=group_m, grid=12)
+    assert r.ok
+    _check(c, _ref(a, b), K)
