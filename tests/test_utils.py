@@ -1,0 +1,48 @@
+"""Roofline arithmetic, clock-sample parsing, stream/result plumbing (CPU only)."""
+import ctypes as C
+
+from rocnrdma_b200.utils import roofline as R
+from rocnrdma_b200.utils.clocks import ClockSampler
+
+
+def test_roofline_uses_measured_peaks_and_payload_is_half_of_copy():
+    p = R.measured_peaks()
+    assert p["hbm_gbs"] > 1000 and p["_source"] in ("measured", "fallback")
+    assert R.copy_roofline_gbps({"hbm_gbs": 6578.7}) == 6578.7 / 2
+    # fused pack: 2 B read + 3 x (1 + 1/32) B moved per 2 B of source
+    src = R.fused_pack_roofline_gbps({"hbm_gbs": 6578.7})
+    assert abs(src - 6578.7 * 2 / (2 + 3 * 33 / 32)) < 1e-6
+    assert R.fused_pack_roofline_gbps({"hbm_gbs": 6578.7}, wire_gbs=50.0) == 50.0 * 2 / (33 / 32)   # NIC-bound on a real wire
+    assert R.fraction(50.0, 100.0) == 0.5
+
+
+def test_clock_sampler_summary_flags_throttle_reasons():
+    s = ClockSampler()
+    s.rows = [dict(index=0, sm=1965.0, sm_max=1965.0, power=400.0, active="0x0", hw_slowdown="Not Active", hw_thermal="Not Active",
+                   sw_thermal="Not Active", sw_power="Active"),
+              dict(index=0, sm=1300.0, sm_max=1965.0, power=990.0, active="0x4", hw_slowdown="Not Active", hw_thermal="Not Active",
+                   sw_thermal="Not Active", sw_power="Active"),
+              dict(index=0, sm=1400.0, sm_max=1965.0, power=980.0, active="0x4", hw_slowdown="Active", hw_thermal="Not Active",
+                   sw_thermal="Not Active", sw_power="Not Active")]
+    out = s.summary()
+    assert out["sm_mhz"] == 1400.0 and out["sm_max_mhz"] == 1965.0 and out["samples"] == 3
+    assert out["reasons"] == ["hw_slowdown", "sw_power_cap"]
+    assert ClockSampler().summary()["samples"] == 0
+
+
+def test_stream_result_arithmetic():
+    from rocnrdma_b200.ops.rdma import StreamResult, parse_stream_out
+    r = StreamResult(status=["OK", "OK"], t_start_ns=[1000, 1100], t_end_ns=[3000, 3100], done=[4, 4], bytes_per_msg=1 << 20)
+    assert r.ok and r.device_ns == 2100 and abs(r.gbps - 8 * (1 << 20) / 2100) < 1e-9 and abs(r.us_per_msg - 2.1 / 4) < 1e-9
+    buf = (C.c_uint8 * 128)()
+    words = (C.c_int64 * 16).from_buffer(buf)
+    words[0], words[1], words[2], words[3] = -1, 5, 9, 3         # CTA 0 timed out
+    words[8], words[9], words[10], words[11] = 0, 6, 10, 7
+    p = parse_stream_out(buf, 2, 64)
+    assert p.status == ["TIMEOUT", "OK"] and not p.ok and p.done == [3, 7] and p.device_ns == 5
+
+
+def test_pack_and_gemm_record_geometry():
+    from rocnrdma_b200.ops import gemm, pack
+    assert pack.record_bytes(1 << 22) == (1 << 22) + (1 << 17)
+    assert gemm.panel_record_bytes(8192) == 128 * 8192 * 33 // 32
