@@ -62,6 +62,12 @@ def main():
                 ops.rdma_stream(qd, op, l, r, size, iters=min(iters, 32), window=win, slot_stride=size, nslots=nslots)
                 res = ops.rdma_stream(qd, op, l, r, size, iters=iters, window=win, slot_stride=size, nslots=nslots, timeout_ms=5000)
                 row[name] = {"ok": res.ok, "gbps": round(res.gbps, 3), "us_per_msg": round(res.us_per_msg, 3)}
+            # perftest-style posting: --post_list 16 --cq-mod 16, 128 outstanding (ib_write_bw's own default is cq-mod 100)
+            for name, op, l, r in (("gpu_posted_burst", W.OP_RDMA_WRITE, ms, md), ("gpu_posted_read_burst", W.OP_RDMA_READ, md, ms)):
+                kw = dict(window=128, burst=16, signal_every=16, slot_stride=size, nslots=nslots)
+                ops.rdma_stream(qd, op, l, r, size, iters=min(iters, 128), **kw)
+                res = ops.rdma_stream(qd, op, l, r, size, iters=iters, timeout_ms=5000, **kw)
+                row[name] = {"ok": res.ok, "gbps": round(res.gbps, 3), "us_per_msg": round(res.us_per_msg, 3)}
             lat = ops.rdma_stream(qd, W.OP_RDMA_WRITE, ms, md, size, iters=min(iters, 64), window=1, slot_stride=size, nslots=nslots)
             row["gpu_posted"]["latency_us"] = round(lat.us_per_msg, 2)
             ns, err = C.c_uint64(), C.c_uint32()

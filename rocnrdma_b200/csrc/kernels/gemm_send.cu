@@ -40,10 +40,13 @@ constexpr int kThreads = 192;
 constexpr int kEpiThreads = 128;
 constexpr uint32_t kTmemCols = 512;                                // two 256-column accumulators
 constexpr unsigned long long kWaitNs = 2000000000ull;
+constexpr int kStageC = 32 * 128;                                  // one TMA-store box: 32 rows x 64 bf16, SWIZZLE_128B
+constexpr uint32_t kFlagDirect = 1, kFlagPlainStores = 2;
 
 struct alignas(1024) Smem {
   uint8_t a[STAGES][A_STAGE];
   uint8_t b[STAGES][B_STAGE];
+  uint8_t stage_c[4][2][kStageC];                                  // epilogue staging: per warp, 2 x (32 rows x 128 B)
   alignas(8) uint64_t full[STAGES], empty[STAGES], tfull[2], tempty[2];
   uint32_t tmem_base;
   volatile int abort;
@@ -59,6 +62,10 @@ struct GemmArgs {
   uint32_t signal_every;
   uint32_t with_imm;         // 1: RDMA_WRITE_IMM, immediate = panel index (wakes a consumer on the receiving GPU)
   uint32_t out_fp8;          // 1: epilogue emits block-scaled fp8 panel records instead of bf16 rows (see below)
+  uint32_t plain_stores;     // 1: bf16 epilogue writes rows with per-thread 16-byte stores instead of staged TMA stores (A/B switch)
+  uint32_t direct;           // 1: `c` IS the peer's registered buffer (NVLink-mapped): the epilogue's stores are the transfer;
+                             //    each finished panel is announced by a zero-length RDMA_WRITE_IMM posted after a cumulative
+                             //    system-scope fence (data plane = SM stores over NVLink, control plane = the RDMA queue pair)
   uint32_t group_m;          // tile rasterisation: this many M blocks advance together across N (L2 reuse of B)
   unsigned int* counters;    // [0..m_blks): tiles done per panel ; [m_blks]: CTAs done
   unsigned long long* acc;   // [0] max idx+1, [1] posted, [2] ~first post time
@@ -152,6 +159,44 @@ __device__ __forceinline__ uint32_t pack_bf16(uint32_t lo_f32, uint32_t hi_f32) 
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// bf16 output.  Each epilogue warp owns 32 accumulator rows; per 64-column chunk it converts its rows to
+// bf16, lays them into a 4 KiB shared-memory box in the SWIZZLE_128B pattern (16-byte piece j of row r sits
+// at piece j ^ (r % 8): conflict-free for the row-per-thread writes) and one lane issues a TMA tensor store.
+// The store leaves the SM as whole 128-byte lines, which is what makes the epilogue usable over NVLink
+// (`direct` mode: per-thread 16-byte row stores reach a peer as 32 separate small packets per instruction
+// -- measured 167 GB/s) and keeps 4x fewer L2 write transactions locally.  Two boxes per warp ping-pong.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(s32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void epilogue_rows_tma(uint8_t (*stage)[kStageC], const CUtensorMap* mc, uint32_t taddr, int col0, int row0, int lane) {
+#pragma unroll 1
+  for (int c = 0; c < BN / 64; ++c) {
+    const uint32_t buf = s32(stage[c & 1]);
+    if (lane == 0) bulk_wait_read1();                 // the store issued from this box two chunks ago has read it
+    __syncwarp();
+    uint32_t r[64];
+    tmem_ld32(taddr + c * 64, r);
+    tmem_ld32(taddr + c * 64 + 32, r + 32);
+    tmem_ld_wait();
+    const uint32_t rowp = buf + lane * 128;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      st_shared_v4(rowp + ((uint32_t)(j ^ (lane & 7)) << 4), pack_bf16(r[8 * j], r[8 * j + 1]), pack_bf16(r[8 * j + 2], r[8 * j + 3]),
+                   pack_bf16(r[8 * j + 4], r[8 * j + 5]), pack_bf16(r[8 * j + 6], r[8 * j + 7]));
+    fence_async_smem();                                // my generic-proxy writes -> visible to the async proxy
+    __syncwarp();
+    if (lane == 0) { tma_store_2d(mc, stage[c & 1], col0 + c * 64, row0); bulk_commit(); }
+  }
+}
+
 // fp8 output (out_fp8 = 1).  One tcgen05.ld 32x32b.x32 hands each epilogue thread 32 consecutive columns
 // of one row -- exactly one MX block -- so the block scale is a register-only reduction: amax over the
 // thread's 32 fp32 accumulators, UE8M0 exponent e (smallest power of two with amax / 2^e <= 448, the same
@@ -180,9 +225,34 @@ __device__ __forceinline__ void quantize_block(const uint32_t* r, uint4* q_out, 
   *scale_out = (uint8_t)(e + 127);
 }
 
+// Panel accounting, run by ONE thread after all 128 rows of a tile are written: the CTA that completes a
+// 128-row panel's last tile posts the panel (or, in direct mode, its zero-length announcement).
+__device__ __forceinline__ void panel_tile_done(const GemmArgs& g, uint32_t m_blk, uint32_t n_blks, bool sys) {
+  fence_gpu();
+  unsigned int old = atomicAdd(&g.counters[m_blk], 1u);
+  if (old + 1 != n_blks) return;
+  fence_scope(sys || g.direct);   // cumulative: covers the other CTAs' tiles of this panel (system scope when they went to a peer)
+  const uint64_t full_bytes = g.out_fp8 ? panel_record_bytes(g.N) : (uint64_t)BM * g.N * 2, off = (uint64_t)m_blk * full_bytes;
+  const uint64_t panel_bytes = g.direct ? 0 : full_bytes;
+  unsigned long long idx = sq_reserve(g.qp, 1, g.timeout_ns);
+  const bool sig = g.signal_every <= 1 || ((idx + 1) % g.signal_every == 0);
+  if (idx != ~0ull) {
+    write_rdma_wqe(g.qp, idx, g.with_imm ? OP_RDMA_WRITE_IMM : OP_RDMA_WRITE, g.c_va + off, g.lkey, g.remote_va + off, g.rkey,
+                   (uint32_t)panel_bytes, sig ? CTRL_CQ_UPDATE : 0, m_blk);
+    if (sq_submit(g.qp, idx, 1, g.timeout_ns, true) == WAIT_OK) {
+      atomicMax(&g.acc[0], idx + 1);
+      atomicAdd(&g.acc[1], 1ull);
+      atomicMax(&g.acc[2], ~globaltimer_ns());
+    } else g.out[0] = (unsigned long long)(long long)WAIT_TIMEOUT;
+  } else g.out[0] = (unsigned long long)(long long)WAIT_TIMEOUT;
+  g.counters[m_blk] = 0;
+}
+__device__ __forceinline__ void bulk_wait_keep4() { asm volatile("cp.async.bulk.wait_group 4;" ::: "memory"); }
+
 // ------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_send_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmArgs g) {
+gemm_send_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_c, GemmArgs g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -254,6 +324,8 @@ gemm_send_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint32_t q = warp & 3;
     uint32_t acc = 0, acc_phase = 0;
     const bool sys = g.qp != nullptr && poster_sys(g.qp);
+    const bool defer = !g.out_fp8 && !g.plain_stores;
+    uint32_t pending = ~0u;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       uint32_t m_blk, n_blk;
       tile_coords(tile, m_blks, n_blks, g.group_m, &m_blk, &n_blk);
@@ -262,7 +334,9 @@ gemm_send_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const uint32_t row_in_panel = q * 32 + lane;
       const uint32_t row = m_blk * BM + row_in_panel;
       const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * BN;
-      if (!g.out_fp8) {
+      if (!g.out_fp8 && !g.plain_stores) {
+        epilogue_rows_tma(s.stage_c[q], &tmap_c, taddr, (int)(n_blk * BN), (int)(m_blk * BM + q * 32), lane);
+      } else if (!g.out_fp8) {
         __nv_bfloat16* crow = g.c + (size_t)row * g.N + (size_t)n_blk * BN;
 #pragma unroll 2
         for (int c = 0; c < BN / 32; ++c) {
@@ -292,29 +366,25 @@ gemm_send_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       if (lane == 0) mbar_arrive(&s.tempty[acc]);                             // 4 arrivals hand the buffer back
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       if (g.qp != nullptr) {
-        // ---- panel accounting: the last tile of a 128-row panel sends it
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");       // all 128 rows of this tile are stored
-        if (threadIdx.x == 64) {
-          fence_gpu();
-          unsigned int old = atomicAdd(&g.counters[m_blk], 1u);
-          if (old + 1 == n_blks) {
-            fence_scope(sys);   // cumulative: covers the other CTAs' tiles of this panel
-            const uint64_t panel_bytes = g.out_fp8 ? panel_record_bytes(g.N) : (uint64_t)BM * g.N * 2, off = (uint64_t)m_blk * panel_bytes;
-            unsigned long long idx = sq_reserve(g.qp, 1, g.timeout_ns);
-            const bool sig = g.signal_every <= 1 || ((idx + 1) % g.signal_every == 0);
-            if (idx != ~0ull) {
-              write_rdma_wqe(g.qp, idx, g.with_imm ? OP_RDMA_WRITE_IMM : OP_RDMA_WRITE, g.c_va + off, g.lkey, g.remote_va + off, g.rkey, (uint32_t)panel_bytes,
-                             sig ? CTRL_CQ_UPDATE : 0, m_blk);
-              if (sq_submit(g.qp, idx, 1, g.timeout_ns, true) == WAIT_OK) {
-                atomicMax(&g.acc[0], idx + 1);
-                atomicAdd(&g.acc[1], 1ull);
-                atomicMax(&g.acc[2], ~globaltimer_ns());
-              } else g.out[0] = (unsigned long long)(long long)WAIT_TIMEOUT;
-            } else g.out[0] = (unsigned long long)(long long)WAIT_TIMEOUT;
-            g.counters[m_blk] = 0;
+        // ---- panel accounting.  With staged TMA stores it runs ONE TILE LATE: tile i's four store groups
+        // stay in flight (a peer acknowledges them microseconds later) while tile i-1 is accounted for.
+        if (defer) {
+          if (pending != ~0u) {
+            if (lane == 0) bulk_wait_keep4();
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+            if (threadIdx.x == 64) panel_tile_done(g, pending, n_blks, sys);
           }
+          pending = m_blk;
+        } else {
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");     // all 128 rows of this tile are stored
+          if (threadIdx.x == 64) panel_tile_done(g, m_blk, n_blks, sys);
         }
       }
+    }
+    if (lane == 0) bulk_wait_all();                                             // staged rows have left shared memory (and are written)
+    if (pending != ~0u && !s.abort) {
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      if (threadIdx.x == 64) panel_tile_done(g, pending, n_blks, sys);
     }
   }
 
@@ -374,6 +444,7 @@ constexpr int BH_STAGE = (BN / 2) * BK * 2;     // half of the B tile: 16 KiB
 struct alignas(1024) Smem2 {
   uint8_t a[STAGES2][A_STAGE];
   uint8_t b[STAGES2][BH_STAGE];
+  uint8_t stage_c[4][2][kStageC];
   alignas(8) uint64_t full[STAGES2], empty[STAGES2], tfull[2], tempty[2];
   uint32_t tmem_base;
   volatile int abort;
@@ -421,7 +492,8 @@ __device__ __forceinline__ bool mbar_wait_t(S& s, uint64_t* b, uint32_t parity) 
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-gemm_send2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmArgs g) {
+gemm_send2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const __grid_constant__ CUtensorMap tmap_c, GemmArgs g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Smem2& s = *reinterpret_cast<Smem2*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -500,6 +572,8 @@ gemm_send2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const uint32_t q = warp & 3;
     uint32_t acc = 0, acc_phase = 0;
     const bool sys = g.qp != nullptr && poster_sys(g.qp);
+    const bool defer = !g.out_fp8 && !g.plain_stores;
+    uint32_t pending = ~0u;
     for (uint32_t tile = cluster_id; tile < n_tiles; tile += n_clusters) {
       uint32_t mp, n_blk;
       tile_coords(tile, mp_blks, n_blks, g.group_m, &mp, &n_blk);
@@ -509,7 +583,9 @@ gemm_send2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const uint32_t row_in_panel = q * 32 + lane;
       const uint32_t row = m_blk * BM + row_in_panel;
       const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * BN;
-      if (!g.out_fp8) {
+      if (!g.out_fp8 && !g.plain_stores) {
+        epilogue_rows_tma(s.stage_c[q], &tmap_c, taddr, (int)(n_blk * BN), (int)(m_blk * BM + q * 32), lane);
+      } else if (!g.out_fp8) {
         __nv_bfloat16* crow = g.c + (size_t)row * g.N + (size_t)n_blk * BN;
 #pragma unroll 2
         for (int c = 0; c < BN / 32; ++c) {
@@ -542,27 +618,25 @@ gemm_send2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       if (g.qp != nullptr) {
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-        if (threadIdx.x == 64) {
-          fence_gpu();
-          unsigned int old = atomicAdd(&g.counters[m_blk], 1u);
-          if (old + 1 == n_blks) {
-            fence_scope(sys);
-            const uint64_t panel_bytes = g.out_fp8 ? panel_record_bytes(g.N) : (uint64_t)BM * g.N * 2, off = (uint64_t)m_blk * panel_bytes;
-            unsigned long long idx = sq_reserve(g.qp, 1, g.timeout_ns);
-            const bool sig = g.signal_every <= 1 || ((idx + 1) % g.signal_every == 0);
-            if (idx != ~0ull) {
-              write_rdma_wqe(g.qp, idx, g.with_imm ? OP_RDMA_WRITE_IMM : OP_RDMA_WRITE, g.c_va + off, g.lkey, g.remote_va + off, g.rkey,
-                             (uint32_t)panel_bytes, sig ? CTRL_CQ_UPDATE : 0, m_blk);
-              sq_submit(g.qp, idx, 1, g.timeout_ns, true);
-              atomicMax(&g.acc[0], idx + 1);
-              atomicAdd(&g.acc[1], 1ull);
-              atomicMax(&g.acc[2], ~globaltimer_ns());
-            } else g.out[0] = (unsigned long long)(long long)WAIT_TIMEOUT;
-            g.counters[m_blk] = 0;
+        // ---- panel accounting.  With staged TMA stores it runs ONE TILE LATE: tile i's four store groups
+        // stay in flight (a peer acknowledges them microseconds later) while tile i-1 is accounted for.
+        if (defer) {
+          if (pending != ~0u) {
+            if (lane == 0) bulk_wait_keep4();
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+            if (threadIdx.x == 64) panel_tile_done(g, pending, n_blks, sys);
           }
+          pending = m_blk;
+        } else {
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");     // all 128 rows of this tile are stored
+          if (threadIdx.x == 64) panel_tile_done(g, m_blk, n_blks, sys);
         }
       }
+    }
+    if (lane == 0) bulk_wait_all();                                             // staged rows have left shared memory (and are written)
+    if (pending != ~0u && !s.abort) {
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      if (threadIdx.x == 64) panel_tile_done(g, pending, n_blks, sys);
     }
   }
 
@@ -616,7 +690,7 @@ EncodeTiledFn encode_tiled() {
   }
   return fn;
 }
-// row-major [rows, K] bf16, box = [box_rows, 64], 128-byte swizzle
+// row-major [rows, K] bf16, box = [box_rows, 64], 128-byte swizzle (operand loads, and the C store map with 32-row boxes)
 int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t K, uint32_t box_rows) {
   EncodeTiledFn fn = encode_tiled();
   if (!fn) return -38;
@@ -638,17 +712,19 @@ RN_API uint32_t rn_gemm_tile(uint32_t* bm, uint32_t* bn, uint32_t* bk) { *bm = B
 // counters_dev: >= (M/128 + 1) * 4 + 32 bytes of zeroed device scratch (self-cleaning), out_dev: 64 B mapped pinned.
 RN_API int rn_k_gemm_send(uint64_t stream, int grid, uint64_t a, uint64_t b, uint64_t c, uint32_t M, uint32_t N, uint32_t K,
                           uint64_t qp_dev, uint64_t c_va, uint32_t lkey, uint64_t remote_va, uint32_t rkey,
-                          uint32_t signal_every, uint32_t with_imm, uint32_t out_fp8, uint32_t cta_group, uint32_t group_m, uint64_t counters_dev,
+                          uint32_t signal_every, uint32_t with_imm, uint32_t out_fp8, uint32_t cta_group, uint32_t group_m, uint32_t flags, uint64_t counters_dev,
                           uint64_t out_dev, uint64_t timeout_ms) {
   if (!M || !N || !K || M % BM || N % BN || K % BK) return -22;
   if ((a | b | c) & 15) return -22;
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, mc;
   int rc = make_map(&ma, (const void*)a, M, K, BM);
   if (!rc) rc = make_map(&mb, (const void*)b, N, K, BN);
+  if (!rc) rc = make_map(&mc, (const void*)c, M, N, 32);           // only dereferenced by the bf16 TMA-store epilogue
   if (rc) return rc;
   GemmArgs g;
   g.c = (__nv_bfloat16*)c; g.M = M; g.N = N; g.K = K; g.qp = (QpDev*)qp_dev; g.c_va = c_va; g.lkey = lkey; g.rkey = rkey;
   g.remote_va = remote_va; g.signal_every = signal_every ? signal_every : 1; g.with_imm = with_imm; g.out_fp8 = out_fp8; g.group_m = group_m ? group_m : 1;
+  g.direct = (flags & kFlagDirect) ? 1 : 0; g.plain_stores = (flags & kFlagPlainStores) ? 1 : 0;
   const uint32_t m_blks = M / BM;
   g.counters = (unsigned int*)counters_dev;
   g.acc = (unsigned long long*)(counters_dev + (((uint64_t)m_blks + 1) * 4 + 7) / 8 * 8);
@@ -668,7 +744,7 @@ RN_API int rn_k_gemm_send(uint64_t stream, int grid, uint64_t a, uint64_t b, uin
     const size_t smem = sizeof(Smem2) + 1024;
     cudaError_t e = cudaFuncSetAttribute(gemm_send2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return -(int)e - 1000;
-    gemm_send2_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ma, mb, g);
+    gemm_send2_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ma, mb, mc, g);
     return (int)cudaGetLastError();
   }
   const uint32_t n_tiles = m_blks * (N / BN);
@@ -676,7 +752,7 @@ RN_API int rn_k_gemm_send(uint64_t stream, int grid, uint64_t a, uint64_t b, uin
   const size_t smem = sizeof(Smem) + 1024;
   cudaError_t e = cudaFuncSetAttribute(gemm_send_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return -(int)e - 1000;
-  gemm_send_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ma, mb, g);
+  gemm_send_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ma, mb, mc, g);
   return (int)cudaGetLastError();
 }
 

@@ -19,9 +19,12 @@ from ..api import Context
 
 @dataclass
 class SendRecvResult:
+    mode: str
     ok: bool
     fused_us: float
     compute_us: float
+    first_post_us: float
+    engine_ctas: int
     unfused_us: float
     tflops: float
     wire_gbps: float
@@ -30,7 +33,11 @@ class SendRecvResult:
     verified: bool
 
 
-def run(M: int = 8192, N: int = 8192, K: int = 2048, engine_ctas: int = 32, gpus=(0, 1), reps: int = 3) -> SendRecvResult:
+def run(M: int = 8192, N: int = 8192, K: int = 2048, engine_ctas: int = 0, gpus=(0, 1), reps: int = 3,
+        mode: str = "engine") -> SendRecvResult:
+    """mode="engine": panels are staged in GPU0's send buffer and moved by the DMA engine (RDMA semantics).
+    mode="direct": the GEMM epilogue stores straight into GPU1's registered buffer over NVLink and only the
+    per-panel completion signal (zero-length RDMA_WRITE_IMM) goes through the queue pair."""
     g0, g1 = gpus
     d0, d1 = torch.device("cuda", g0), torch.device("cuda", g1)
     tx, rx = Context(g0), Context(g1)
@@ -49,6 +56,11 @@ def run(M: int = 8192, N: int = 8192, K: int = 2048, engine_ctas: int = 32, gpus
     qa.connect(qb)
     qa.set_flags(sys_scope=True)                # the responder side of this QP lives on another GPU
     torch.cuda.synchronize(d0); torch.cuda.synchronize(d1)
+    direct = mode == "direct"
+    if engine_ctas <= 0:
+        engine_ctas = 8 if direct else 32          # direct: the engine only carries the signals
+    if direct:
+        d_local = tx.reg_mr(d)                     # GPU1's buffer, registered with GPU0's HCA: peer mapping over NVLink
     tx.engine_start(ctas=engine_ctas, idle_timeout_ms=5000)
     grid = 148 - engine_ctas
     best = None
@@ -57,7 +69,11 @@ def run(M: int = 8192, N: int = 8192, K: int = 2048, engine_ctas: int = 32, gpus
             for _ in range(panels):
                 qb.post_recv(dm, 0)
             view, rstream = ops.recv_consume(qb, panels, panels, stamps, timeout_ms=5000, sync=False)
-            r = ops.gemm_send(tx, a, b, c, c_mr=cm, qp=qa, dst_mr=dm, signal_every=4, with_imm=True, grid=grid, timeout_ms=5000)
+            if direct:
+                r = ops.gemm_send(tx, a, b, d, c_mr=d_local, qp=qa, dst_mr=dm, signal_every=4, with_imm=True, direct=True,
+                                  grid=grid, timeout_ms=5000)
+            else:
+                r = ops.gemm_send(tx, a, b, c, c_mr=cm, qp=qa, dst_mr=dm, signal_every=4, with_imm=True, grid=grid, timeout_ms=5000)
             rstream.synchronize()
             cons = ops.parse_recv(view)
             if best is None or r.device_ns < best[0].device_ns:
@@ -74,9 +90,12 @@ def run(M: int = 8192, N: int = 8192, K: int = 2048, engine_ctas: int = 32, gpus
     finally:
         tx.engine_stop()
     r, cons = best
+    if direct:
+        ops.gemm_send(tx, a, b, c)                 # reference product computed locally for the comparison
     verified = bool(torch.equal(c.cpu(), d.cpu()))
-    out = SendRecvResult(ok=r.ok and cons["status"] == "OK" and cons["seen"] == panels, fused_us=r.device_ns / 1e3,
-                         compute_us=(r.t_compute_end_ns - r.t_start_ns) / 1e3, unfused_us=unfused_us, tflops=r.tflops,
+    out = SendRecvResult(mode=mode, ok=r.ok and cons["status"] == "OK" and cons["seen"] == panels, fused_us=r.device_ns / 1e3,
+                         compute_us=(r.t_compute_end_ns - r.t_start_ns) / 1e3,
+                         first_post_us=(r.t_first_post_ns - r.t_start_ns) / 1e3, engine_ctas=engine_ctas, unfused_us=unfused_us, tflops=r.tflops,
                          wire_gbps=r.wire_gbps, panels=panels, consumer=cons, verified=verified)
     tx.close(); rx.close()
     return out
@@ -86,5 +105,5 @@ if __name__ == "__main__":
     import json
     import sys
     shape = tuple(int(x) for x in sys.argv[1:4]) if len(sys.argv) >= 4 else (8192, 8192, 2048)
-    res = run(*shape)
+    res = run(*shape, mode=sys.argv[4] if len(sys.argv) > 4 else "engine", engine_ctas=int(sys.argv[5]) if len(sys.argv) > 5 else 0)
     print(json.dumps(res.__dict__))

@@ -69,13 +69,17 @@ def dequant_fp8_panels(rec: torch.Tensor, M: int, Nn: int) -> torch.Tensor:
 
 
 def gemm_send(ctx, a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, c_mr=None, qp=None, dst_mr=None,
-              signal_every: int = 1, with_imm: bool = False, out_fp8: bool = False, cta_group: int = 0, group_m: int = 0, grid: int = 0, timeout_ms: int = 2000, stream=None, sync: bool = True,
+              signal_every: int = 1, with_imm: bool = False, out_fp8: bool = False, cta_group: int = 0, group_m: int = 0, direct: bool = False, plain_stores: bool = False, grid: int = 0, timeout_ms: int = 2000, stream=None, sync: bool = True,
               scratch_slot: int = 2):
     """``c[M,N] = a[M,K] @ b[N,K].T`` (bf16 in/out, fp32 accumulate on the 5th-gen tensor cores).
 
     With ``qp``/``c_mr``/``dst_mr`` every finished 128-row panel of ``c`` is RDMA-written to the same
     offset of ``dst_mr`` from inside the kernel; the call returns when the last panel has landed.
     Shapes must be multiples of the tile: M % 128 == 0, N % 256 == 0, K % 64 == 0.
+    ``direct``: ``c`` is itself the peer's registered buffer (a tensor on the other GPU): the epilogue stores
+    rows over NVLink and each panel is announced by a zero-length RDMA_WRITE_IMM (needs ``qp``, ``c_mr`` = the
+    peer region as seen locally, ``dst_mr``).
+    ``plain_stores``: bf16 epilogue with per-thread row stores instead of staged TMA tensor stores (A/B switch).
     ``group_m``: M blocks that advance together across N (L2 reuse of B; 0 = 8 for compute only, 4 when sending).
     ``cta_group``: 2 = CTA-pair kernel (256x256 tiles, the B operand shared across the pair; measured
     1.05-1.11x cuBLAS at 4096^3 .. 16384x4096x1024), 1 = single-CTA 128x256 kernel, 0 (default) = the pair
@@ -109,7 +113,7 @@ def gemm_send(ctx, a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, c_mr=None,
     rc = lib.rn_k_gemm_send(_stream_ptr(ws), grid, a.data_ptr(), b.data_ptr(), c.data_ptr(), M, Nn, K,
                             qp.dev_ptr if qp is not None else 0, c_mr.addr if c_mr is not None else 0,
                             c_mr.lkey if c_mr is not None else 0, dst_mr.addr if dst_mr is not None else 0,
-                            dst_mr.rkey if dst_mr is not None else 0, signal_every, int(with_imm), int(out_fp8), cta_group, group_m, counters, out_addr, timeout_ms)
+                            dst_mr.rkey if dst_mr is not None else 0, signal_every, int(with_imm), int(out_fp8), cta_group, group_m, int(direct) | (2 if plain_stores else 0), counters, out_addr, timeout_ms)
     if rc:
         raise N.NativeError(f"gemm_send launch failed ({rc})")
     if not sync:

@@ -56,10 +56,12 @@ class StreamResult:
 
 
 def rdma_stream(qps, opcode: int, src_mr, dst_mr, nbytes: int, iters: int = 1, window: int = 0,
-                signal_every: int = 1, stride: int = 0, slot_stride: int = 0, nslots: int = 1,
+                signal_every: int = 1, burst: int = 1, stride: int = 0, slot_stride: int = 0, nslots: int = 1,
                 timeout_ms: int = 2000, stream=None, sync: bool = True, out=None):
     """Launch the device poster: one CTA per QP posts ``iters`` work requests of
     ``nbytes`` (window-limited), polls its CQ on the device and returns device times.
+    ``burst`` work requests share one slot reservation and one doorbell (perftest ``--post_list``),
+    ``signal_every`` is the CQ moderation (``--cq-mod``); both are clamped so the window can always drain.
 
     For RDMA_READ ``src_mr`` is the local destination and ``dst_mr`` the remote source,
     mirroring the laddr/raddr roles in the WQE.
@@ -74,7 +76,7 @@ def rdma_stream(qps, opcode: int, src_mr, dst_mr, nbytes: int, iters: int = 1, w
     out_addr, out_view = ctx.scratch(nq * 64) if out is None else out
     rc = lib.rn_k_rdma_stream(_stream_ptr(ws), qp_arr, nq, opcode, src_mr.addr, src_mr.lkey,
                               dst_mr.addr if dst_mr is not None else 0, dst_mr.rkey if dst_mr is not None else 0,
-                              stride, nbytes, iters, window, signal_every, slot_stride, nslots, timeout_ms, out_addr)
+                              stride, nbytes, iters, window, signal_every, burst, slot_stride, nslots, timeout_ms, out_addr)
     if rc:
         raise N.NativeError(f"rdma_stream launch failed: cuda error {rc}")
     if not sync:

@@ -58,3 +58,13 @@ def test_cross_process_ring_over_cuda_ipc(tmp_path):
     res = json.loads(out.read_text())
     assert res["verified"] and res["world"] == 2
     assert res["rows"][-1]["per_gpu_gbps"] > 200
+
+
+def test_config4_direct_mode_epilogue_stores_over_nvlink():
+    """GEMM epilogue writes straight into GPU1's buffer; only the per-panel signal uses the queue pair."""
+    _need2()
+    from rocnrdma_b200.models import sendrecv_gemm
+    res = sendrecv_gemm.run(M=1024, N=1024, K=1024, reps=2, mode="direct")
+    assert res.ok, res
+    assert res.verified
+    assert res.consumer["seen"] == 8 and res.consumer["bytes"] == 0      # zero-length signals

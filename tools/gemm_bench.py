@@ -30,7 +30,8 @@ for (M, N, K) in shapes:
     for _ in range(2): ops.gemm_send(ctx, a, b, c, cta_group=2)
     best2 = max(ops.gemm_send(ctx, a, b, c, cta_group=2).tflops for _ in range(5))
     gm = {g: round(max(ops.gemm_send(ctx, a, b, c, cta_group=2, group_m=g).tflops for _ in range(3)), 1) for g in (1, 2, 4, 8, 16)}
-    row = dict(M=M, N=N, K=K, group_m_sweep_2cta=gm, cublas_tflops=round(cublas_tf, 1), ours_1cta_tflops=round(best, 1), frac_1cta=round(best / cublas_tf, 3),
+    plain2 = max(ops.gemm_send(ctx, a, b, c, cta_group=2, plain_stores=True).tflops for _ in range(5))
+    row = dict(M=M, N=N, K=K, group_m_sweep_2cta=gm, ours_2cta_plain_store_epilogue_tflops=round(plain2, 1), cublas_tflops=round(cublas_tf, 1), ours_1cta_tflops=round(best, 1), frac_1cta=round(best / cublas_tf, 3),
                ours_2cta_tflops=round(best2, 1), frac_2cta=round(best2 / cublas_tf, 3))
     for ectas in [16]:
         ctx.engine_start(ctas=ectas, idle_timeout_ms=3000)
