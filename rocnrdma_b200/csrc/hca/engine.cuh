@@ -80,17 +80,25 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // ------------------------------------------------------------------ MKey lookup
 // Returns the engine-reachable pointer for [addr, addr+len) under `key`, or 0 with
 // *syn set.  need = access bits that must all be present.
-__device__ __forceinline__ uint64_t translate(const MKeyEntry* tab, uint32_t n, uint32_t key, uint64_t addr,
-                                              uint32_t len, uint32_t need, bool remote, uint8_t* syn) {
-  uint32_t idx = key >> 8;
-  if (idx >= n) { *syn = remote ? SYN_REMOTE_ACCESS_ERR : SYN_LOCAL_PROT_ERR; return 0; }
-  const MKeyEntry* e = tab + idx;
-  uint4 a = ld_v4_volatile(e);                                   // base, len
-  uint4 b = ld_v4_volatile(reinterpret_cast<const uint8_t*>(e) + 16);  // map_base, key, access
-  uint4 c = ld_v4_volatile(reinterpret_cast<const uint8_t*>(e) + 32);             // valid, kind
-  uint64_t base = ((uint64_t)a.y << 32) | a.x, mlen = ((uint64_t)a.w << 32) | a.z;
-  uint64_t map_base = ((uint64_t)b.y << 32) | b.x;
-  uint32_t ekey = b.z, acc = b.w, valid = c.x;
+struct MKeyRaw { uint4 a, b, c; bool in_range; };
+// The three 16-byte loads of one entry, issued without looking at them: a WQE's local and remote key
+// are fetched back to back (one round trip for both; the remote table may sit across NVLink).
+__device__ __forceinline__ MKeyRaw mkey_load(const MKeyEntry* tab, uint32_t n, uint32_t key) {
+  MKeyRaw r;
+  const uint32_t idx = key >> 8;
+  r.in_range = idx < n;
+  const uint8_t* e = reinterpret_cast<const uint8_t*>(tab + (r.in_range ? idx : 0));
+  r.a = ld_v4_volatile(e);        // base, len
+  r.b = ld_v4_volatile(e + 16);   // map_base, key, access
+  r.c = ld_v4_volatile(e + 32);   // valid, kind
+  return r;
+}
+__device__ __forceinline__ uint64_t mkey_check(const MKeyRaw& r, uint32_t key, uint64_t addr, uint32_t len, uint32_t need,
+                                               bool remote, uint8_t* syn) {
+  if (!r.in_range) { *syn = remote ? SYN_REMOTE_ACCESS_ERR : SYN_LOCAL_PROT_ERR; return 0; }
+  const uint64_t base = ((uint64_t)r.a.y << 32) | r.a.x, mlen = ((uint64_t)r.a.w << 32) | r.a.z;
+  const uint64_t map_base = ((uint64_t)r.b.y << 32) | r.b.x;
+  const uint32_t ekey = r.b.z, acc = r.b.w, valid = r.c.x;
   if (!valid || ekey != key) { *syn = remote ? SYN_REMOTE_ACCESS_ERR : SYN_LOCAL_PROT_ERR; return 0; }
   if ((acc & need) != need) { *syn = remote ? SYN_REMOTE_ACCESS_ERR : SYN_LOCAL_ACCESS_ERR; return 0; }
   if (addr < base || addr + len > base + mlen || addr + len < addr) {
@@ -99,6 +107,11 @@ __device__ __forceinline__ uint64_t translate(const MKeyEntry* tab, uint32_t n, 
   }
   if (len == 0) return map_base ? map_base : 1;  // zero-length: any non-null token
   return map_base + (addr - base);
+}
+__device__ __forceinline__ uint64_t translate(const MKeyEntry* tab, uint32_t n, uint32_t key, uint64_t addr,
+                                              uint32_t len, uint32_t need, bool remote, uint8_t* syn) {
+  const MKeyRaw r = mkey_load(tab, n, key);
+  return mkey_check(r, key, addr, len, need, remote, syn);
 }
 
 // ------------------------------------------------------------------ CQE writer
@@ -133,7 +146,7 @@ struct Smem {
   alignas(8) uint64_t full[kStages];
   // work descriptor broadcast from thread 0
   uint64_t src, dst;
-  uint32_t len;
+  uint32_t len, nch;
   int have_work;
   uint32_t phase_bits;   // per-stage parity of the next wait
 };
@@ -141,10 +154,11 @@ struct Smem {
 // Bulk path: thread 0 keeps kStages-kStoresInFlight loads and kStoresInFlight stores in flight.
 // (With a single store in flight every 16 KiB step exposed the store's smem-read latency,
 // ~0.35 us, which capped a CTA near 45 GB/s.)  Requires 16-byte aligned src, dst and len.
+template <int kSif>
 __device__ __forceinline__ bool copy_bulk(Smem& s, uint64_t src, uint64_t dst, uint32_t len) {
   const uint32_t nsub = (len + kSub - 1) / kSub;
   uint32_t phase_bits = s.phase_bits;
-  constexpr int P = kStages - kStoresInFlight;
+  constexpr int P = kStages - kSif;
   auto sub_len = [&](uint32_t i) { return (i + 1 == nsub) ? (len - i * kSub) : kSub; };
   uint32_t issued = 0;
   for (; issued < nsub && issued < (uint32_t)P; ++issued) {
@@ -167,7 +181,7 @@ __device__ __forceinline__ bool copy_bulk(Smem& s, uint64_t src, uint64_t dst, u
     if (issued < nsub) {
       // the stage of load `issued` (= i + P) was last read by store i - kStoresInFlight:
       // stores i .. i-kStoresInFlight+1 may still be pending
-      bulk_wait_read<kStoresInFlight>();
+      bulk_wait_read<kSif>();
       int ls = issued % kStages;
       mbar_expect_tx(&s.full[ls], sub_len(issued));
       bulk_g2s(s.ring[ls], (const void*)(src + (uint64_t)issued * kSub), sub_len(issued), &s.full[ls]);
@@ -226,14 +240,18 @@ __device__ __forceinline__ void parse_wqe(QpDev* qp, unsigned long long w, Parse
     switch (v.opcode) {
       case OP_NOP: v.bytes = 0; break;
       case OP_RDMA_WRITE:
-      case OP_RDMA_WRITE_IMM:
-        p->src = translate(qp->lkeys, qp->n_lkeys, v.lkey, v.laddr, v.bytes, 0, false, &p->syn);
-        if (p->src) p->dst = translate(qp->r.rkeys, qp->r.n_rkeys, v.rkey, v.raddr, v.bytes, ACC_REMOTE_WRITE, true, &p->syn);
+      case OP_RDMA_WRITE_IMM: {
+        const MKeyRaw lk = mkey_load(qp->lkeys, qp->n_lkeys, v.lkey), rk = mkey_load(qp->r.rkeys, qp->r.n_rkeys, v.rkey);
+        p->src = mkey_check(lk, v.lkey, v.laddr, v.bytes, 0, false, &p->syn);
+        if (p->src) p->dst = mkey_check(rk, v.rkey, v.raddr, v.bytes, ACC_REMOTE_WRITE, true, &p->syn);
         break;
-      case OP_RDMA_READ:
-        p->dst = translate(qp->lkeys, qp->n_lkeys, v.lkey, v.laddr, v.bytes, ACC_LOCAL_WRITE, false, &p->syn);
-        if (p->dst) p->src = translate(qp->r.rkeys, qp->r.n_rkeys, v.rkey, v.raddr, v.bytes, ACC_REMOTE_READ, true, &p->syn);
+      }
+      case OP_RDMA_READ: {
+        const MKeyRaw lk = mkey_load(qp->lkeys, qp->n_lkeys, v.lkey), rk = mkey_load(qp->r.rkeys, qp->r.n_rkeys, v.rkey);
+        p->dst = mkey_check(lk, v.lkey, v.laddr, v.bytes, ACC_LOCAL_WRITE, false, &p->syn);
+        if (p->dst) p->src = mkey_check(rk, v.rkey, v.raddr, v.bytes, ACC_REMOTE_READ, true, &p->syn);
         break;
+      }
       case OP_SEND:
       case OP_SEND_IMM:
         p->src = translate(qp->lkeys, qp->n_lkeys, v.lkey, v.laddr, v.bytes, 0, false, &p->syn);
@@ -250,7 +268,8 @@ __device__ __forceinline__ bool needs_recv_wqe(uint8_t opcode) {
 // Publish resolved[w].  Runs in the parallel part for plain RDMA WRITE / READ / NOP and in
 // the ordered part for receive-consuming opcodes.  Returns the number of chunks.
 __device__ __forceinline__ uint32_t write_resolved(QpDev* qp, unsigned long long w, const WqeView& v, uint8_t syn,
-                                                   uint64_t src, uint64_t dst, uint64_t rq_idx, uint8_t rq_taken) {
+                                                   uint64_t src, uint64_t dst, uint64_t rq_idx, uint8_t rq_taken,
+                                                   uint32_t* chunk_out = nullptr) {
   Resolved* r = qp->resolved + (w & ((1u << qp->sq_log) - 1));
   // Work granule: at least the QP's chunk_bytes, grown so that a very large message is cut
   // into ~8 claims per engine CTA (bounded claim traffic, still balances the tail).
@@ -263,6 +282,7 @@ __device__ __forceinline__ uint32_t write_resolved(QpDev* qp, unsigned long long
   }
   uint32_t nchunks = (syn == SYN_OK && v.bytes > 0) ? (v.bytes + chunk - 1) / chunk : 1;
   r->chunk = chunk;
+  if (chunk_out) *chunk_out = chunk;
   r->src = src; r->dst = dst;
   r->bytes = (syn == SYN_OK) ? v.bytes : 0;
   r->nchunks = nchunks;
@@ -328,29 +348,31 @@ __device__ __forceinline__ uint8_t recv_cqe_opcode(uint8_t opc, bool err) {
   return err ? CQE_RESP_ERR : (opc == OP_SEND ? CQE_RESP_SEND : (opc == OP_SEND_IMM ? CQE_RESP_SEND_IMM : CQE_RESP_WR_IMM));
 }
 
-__device__ __forceinline__ void retire(QpDev* qp, uint32_t lane) {
+__device__ __forceinline__ void retire(QpDev* qp, uint32_t lane, unsigned long long w_finished) {
   const uint32_t mask = (1u << qp->sq_log) - 1;
   const bool sys = qp->sys_scope != 0;
   const uint32_t lt = (1u << lane) - 1;
+  // The caller just finished WQE w_finished.  retire_word = (head << 1) | locked, so one CAS answers both
+  // "is it this WQE's turn" and "did I get the lock".  A failed CAS needs no follow-up: either a holder
+  // exists (it re-checks the head slot after unlocking) or an earlier WQE is still unfinished (its
+  // finisher will find this one in its run).
+  unsigned long long h = __shfl_sync(0xffffffffu, w_finished, 0);
   for (;;) {
+    // the state words of the next 32 WQEs travel together with the lock attempt (a stale "not finished"
+    // only shortens the run; the state names its own index, so it can never be stale-positive)
+    unsigned long long st = ld_u64_volatile(&(qp->resolved + ((h + lane) & mask))->state);
     int locked = 0;
-    unsigned long long h = 0;
-    if (lane == 0) {
-      locked = atomicCAS(&qp->retire_lock, 0u, 1u) == 0u;
-      if (locked) {
-        fence_gpu();  // acquire: retire_head and slot states written by the previous holder / finishers
-        h = ld_u64_volatile(&qp->retire_head);
-      }
-    }
-    locked = __shfl_sync(0xffffffffu, locked, 0);
-    if (!locked) return;
-    h = __shfl_sync(0xffffffffu, h, 0);
+    if (lane == 0) locked = atomicCAS(&qp->retire_word, h << 1, (h << 1) | 1ull) == (h << 1);
+    if (!__shfl_sync(0xffffffffu, locked, 0)) return;
+    bool first = true;
     for (;;) {
-      // ---- pass 1: which of the next 32 WQEs are finished (the state word names its own WQE index, so a
-      //      lane that wrapped around a short ring simply sees "not mine")
+      // ---- pass 1: the run of finished WQEs starting at the head (a lane that wrapped around a short ring
+      //      sees a state word that names another index, i.e. "not mine")
       const unsigned long long w = h + lane;
       Resolved* r = qp->resolved + (w & mask);
-      const bool fin = ld_u64_volatile(&r->state) == ((w << 2) | 2ull);
+      if (!first) st = ld_u64_volatile(&r->state);
+      first = false;
+      const bool fin = st == ((w << 2) | 2ull);
       const uint32_t finmask = __ballot_sync(0xffffffffu, fin);
       const int n = finmask == 0xffffffffu ? 32 : __ffs((int)~finmask) - 1;   // leading run
       if (n == 0) break;
@@ -394,16 +416,16 @@ __device__ __forceinline__ void retire(QpDev* qp, uint32_t lane) {
           trace_stamp(qp, w, TR_CQE);
         }
       }
-      // ---- counters (only ever written under the retire lock)
+      // ---- counters: fire-and-forget reductions (nobody waits for them, no stale-line hazard)
       unsigned long long run_bytes = bytes;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) run_bytes += __shfl_xor_sync(0xffffffffu, run_bytes, o);
       const uint32_t n_err = __popc(__ballot_sync(0xffffffffu, err));
       if (lane == 0) {
-        qp->n_cqe = qp->n_cqe + (unsigned)n_send;
-        qp->n_err = qp->n_err + n_err;
-        qp->n_wqe = qp->n_wqe + (unsigned)n;
-        qp->n_bytes = qp->n_bytes + run_bytes;
+        if (n_send) atomicAdd(&qp->n_cqe, (unsigned long long)n_send);
+        if (n_err) atomicAdd(&qp->n_err, (unsigned long long)n_err);
+        atomicAdd(&qp->n_wqe, (unsigned long long)n);
+        if (run_bytes) atomicAdd(&qp->n_bytes, run_bytes);
       }
       h += (unsigned)n;
       if (n < kRetireBatch) break;
@@ -411,14 +433,14 @@ __device__ __forceinline__ void retire(QpDev* qp, uint32_t lane) {
     __syncwarp();   // every lane's tails are ordered before lane 0's release below
     int again = 0;
     if (lane == 0) {
-      *(volatile unsigned long long*)&qp->retire_head = h;
+      *(volatile unsigned long long*)&qp->retire_head = h;   // for observers (idle detection, host queries)
       fence_gpu();  // release
-      atomicExch(&qp->retire_lock, 0u);
+      atomicExch(&qp->retire_word, h << 1);
       __threadfence();  // SC: unlock before re-checking the next slot (store-buffering pattern with finishers)
-      Resolved* r = qp->resolved + (h & mask);
-      again = ld_u64_volatile(&r->state) == ((h << 2) | 2ull);
+      again = ld_u64_volatile(&(qp->resolved + (h & mask))->state) == ((h << 2) | 2ull);
     }
     if (!__shfl_sync(0xffffffffu, again, 0)) return;
+    h = __shfl_sync(0xffffffffu, h, 0);
   }
 }
 
@@ -427,6 +449,9 @@ struct Work {
   QpDev* qp;
   unsigned long long w;
   uint32_t chunk;
+  // filled by a direct (single-WQE) claim, which has just computed them: saves re-reading resolved[w]
+  uint32_t have_desc, len, nch;
+  uint64_t src, dst;
 };
 
 // Draw one chunk from the ticket of the WQE in slot `res`.  `w_hint` is any index whose
@@ -443,7 +468,7 @@ __device__ __forceinline__ bool draw_chunk(QpDev* qp, Resolved* res, unsigned lo
   long long delta = (long long)((gen - (uint32_t)w_hint) & TICKET_FIELD_MASK);
   if (delta >= (long long)(TICKET_FIELD_MASK + 1) / 2) delta -= (long long)(TICKET_FIELD_MASK + 1);
   fence_gpu();  // acquire: resolved[] fields of that generation
-  out->qp = qp; out->w = (unsigned long long)((long long)w_hint + delta); out->chunk = c;
+  out->qp = qp; out->w = (unsigned long long)((long long)w_hint + delta); out->chunk = c; out->have_desc = 0;
   return true;
 }
 
@@ -488,8 +513,9 @@ __device__ __forceinline__ int try_claim(EngineCtl* ctl, QpDev* qp, Work* out, b
       Parsed p;
       parse_wqe(qp, w, &p);
       const bool recv = p.syn == SYN_OK && needs_recv_wqe(p.v.opcode);
-      uint32_t n = 1;
-      if (!recv) n = write_resolved(qp, w, p.v, p.syn, p.src, p.dst, 0, 0);
+      uint32_t n = 1, chunk_sz = 0;
+      uint64_t fsrc = p.src, fdst = p.dst;
+      if (!recv) n = write_resolved(qp, w, p.v, p.syn, p.src, p.dst, 0, 0, &chunk_sz);
       // ---- ordered part: wait for the turn.  The turn word also carries "QP already failed",
       //      so the common path is one poll + one store, no fence.
       unsigned long long turn = ld_u64_volatile(&qp->parse_seq);
@@ -504,13 +530,14 @@ __device__ __forceinline__ int try_claim(EngineCtl* ctl, QpDev* qp, Work* out, b
       if (err) {
         // flushed: nothing moves, whatever the parse said
         syn = SYN_WR_FLUSH_ERR;
-        n = write_resolved(qp, w, p.v, syn, 0, 0, 0, 0);
+        n = write_resolved(qp, w, p.v, syn, 0, 0, 0, 0, &chunk_sz);
       } else if (recv) {
         fence_gpu();  // acquire rq_head from the previous receive-consuming WQE
         uint64_t dst = p.dst, rq_idx = 0;
         uint8_t rq_taken = 0;
         match_recv(ctl, qp, p.v, &syn, &dst, &rq_idx, &rq_taken);
-        n = write_resolved(qp, w, p.v, syn, p.src, dst, rq_idx, rq_taken);
+        n = write_resolved(qp, w, p.v, syn, p.src, dst, rq_idx, rq_taken, &chunk_sz);
+        fdst = dst;
         fence_gpu();  // release rq_head
       }
       if (syn != SYN_OK && !err) { qp->state = QPS_ERR; err = true; }
@@ -525,6 +552,11 @@ __device__ __forceinline__ int try_claim(EngineCtl* ctl, QpDev* qp, Work* out, b
       }
       trace_stamp(qp, w, TR_PARSED);
       out->qp = qp; out->w = w; out->chunk = 0;
+      {
+        const uint32_t bytes = syn == SYN_OK ? p.v.bytes : 0;
+        out->have_desc = 1; out->nch = n; out->src = fsrc; out->dst = fdst;
+        out->len = bytes < chunk_sz ? bytes : chunk_sz;     // chunk 0
+      }
       return 1;
     }
   }
@@ -647,11 +679,18 @@ __global__ void __launch_bounds__(kThreads, 1) engine_kernel(EngineCtl* ctl) {
   // over PCIe starved a concurrent cudaMemcpy (0.9 GB/s).  Helping with an already-parsed WQE only
   // touches device memory, so everybody still does that.
   const bool host_watcher = blockIdx.x == gridDim.x - 1;
+  uint32_t n_qps_cached = ctl->n_qps;
+  unsigned iter = 0;
   for (;;) {
     int batch_k = 0;
     if (threadIdx.x == 0) {
       s.have_work = 0;
-      uint32_t n = ctl->n_qps;
+      // "everybody leaves" travels with the queue scan (its latency hides behind try_claim's loads); the QP
+      // count is re-read every 64 iterations together with the fence that drops stale L1 lines, so host-side
+      // updates (new QPs, reconnects) become visible within ~100 us without a dependent load per iteration
+      const unsigned quit_all_seen = *(volatile unsigned int*)&ctl->quit_all;
+      if ((iter++ & 63u) == 0) { fence_gpu(); n_qps_cached = ctl->n_qps; }
+      const uint32_t n = n_qps_cached;
       bool pending = false;
       if (sticky_qp) {
         Resolved* sr = sticky_qp->resolved + (sticky_w & ((1u << sticky_qp->sq_log) - 1));
@@ -668,14 +707,21 @@ __global__ void __launch_bounds__(kThreads, 1) engine_kernel(EngineCtl* ctl) {
         if (got) rr = (rr + k) % n;
       }
       if (s.have_work) {
-        Resolved* r = work.qp->resolved + (work.w & ((1u << work.qp->sq_log) - 1));
-        uint32_t chunk = *(volatile uint32_t*)&r->chunk;
-        uint64_t off = (uint64_t)work.chunk * chunk;
-        uint32_t bytes = *(volatile uint32_t*)&r->bytes;
-        s.len = bytes == 0 ? 0 : (uint32_t)((bytes - off < chunk) ? (bytes - off) : chunk);
-        s.src = r->src + off;
-        s.dst = r->dst + off;
-        if (*(volatile uint32_t*)&r->nchunks > 1) { sticky_qp = work.qp; sticky_w = work.w; }
+        if (work.have_desc) {
+          s.len = work.len; s.src = work.src; s.dst = work.dst; s.nch = work.nch;
+        } else {
+          Resolved* r = work.qp->resolved + (work.w & ((1u << work.qp->sq_log) - 1));
+          const uint4 f = ld_v4_volatile(reinterpret_cast<const uint8_t*>(r) + 16);   // bytes | nchunks | imm | flags
+          const uint4 a = ld_v4_volatile(reinterpret_cast<const uint8_t*>(r));        // src | dst
+          const uint32_t chunk = *(volatile uint32_t*)&r->chunk;
+          const uint64_t off = (uint64_t)work.chunk * chunk;
+          const uint32_t bytes = f.x;
+          s.len = bytes == 0 ? 0 : (uint32_t)((bytes - off < chunk) ? (bytes - off) : chunk);
+          s.src = (((uint64_t)a.y << 32) | a.x) + off;
+          s.dst = (((uint64_t)a.w << 32) | a.z) + off;
+          s.nch = f.y;
+        }
+        if (s.nch > 1) { sticky_qp = work.qp; sticky_w = work.w; }
         last_activity = globaltimer_ns();
         spins = 0;
       } else {
@@ -684,9 +730,9 @@ __global__ void __launch_bounds__(kThreads, 1) engine_kernel(EngineCtl* ctl) {
         // the engine idle or drained; everybody else follows quit_all.
         if (pending) last_activity = globaltimer_ns();
         else if (host_watcher && ctl->oneshot && spins > 4) { quit = 1; ctl->quit_all = 1; }   // drained: every posted WQE has retired
+        if (quit_all_seen) quit = 1;
         if ((spins & 63) == 0) {
-          fence_gpu();  // drops stale L1 lines: host-side updates (new QPs, reconnects) become visible
-          if (*ctl->stop || *(volatile unsigned int*)&ctl->quit_all) quit = 1;
+          if (*ctl->stop) quit = 1;   // mapped host word: a PCIe read, hence only every 64 idle spins
           else if (host_watcher && globaltimer_ns() - last_activity > ctl->idle_timeout_ns) { quit = 1; ctl->exited_idle = 1; ctl->quit_all = 1; }
         }
         if (spins > 256) __nanosleep(200);
@@ -712,7 +758,9 @@ __global__ void __launch_bounds__(kThreads, 1) engine_kernel(EngineCtl* ctl) {
       const bool bulk = len >= kBulkMin && (((csrc | cdst) & 15) == 0) && ((len & 15) == 0);
       if (bulk) {
         if (threadIdx.x == 0) {
-          if (!copy_bulk(s, csrc, cdst, len)) { ctl->fatal = 1; quit = 1; }
+          const unsigned sif = ctl->stores_in_flight;
+          const bool okc = sif == 8 ? copy_bulk<8>(s, csrc, cdst, len) : (sif == 6 ? copy_bulk<6>(s, csrc, cdst, len) : copy_bulk<4>(s, csrc, cdst, len));
+          if (!okc) { ctl->fatal = 1; quit = 1; }
           atomicAdd(&ctl->n_bulk_chunks, 1ull);
         }
       } else {
@@ -729,11 +777,11 @@ __global__ void __launch_bounds__(kThreads, 1) engine_kernel(EngineCtl* ctl) {
       // when the CQ or the payload lives in host / peer memory: the retirer's system-scope
       // fence in write_cqe() is cumulative over everything this chain of gpu-scope releases made
       // visible to it (a sys fence per chunk cost ~2x on host-resident queues, measured).
-      fence_gpu();
-      const uint32_t nch = r->nchunks;
+      const uint32_t nch = s.nch;
+      if (nch > 1) fence_gpu();   // this chunk's bytes before the count that may complete the WQE
       if (nch == 1 || atomicAdd(&r->done, 1u) + 1 == nch) {
         trace_stamp(qp, work.w, TR_COPIED);
-        fence_gpu();  // observe every other chunk's count -> their bytes precede our CQE
+        fence_gpu();  // single chunk: its bytes before "finished"; else observe every other chunk's count -> their bytes precede our CQE
         *(volatile unsigned long long*)&r->state = (work.w << 2) | 2ull;
         __threadfence();  // SC: "finished" store before the retire try-lock (pairs with the unlock / re-check below)
         finished = 1;
@@ -741,7 +789,7 @@ __global__ void __launch_bounds__(kThreads, 1) engine_kernel(EngineCtl* ctl) {
     }
     if (threadIdx.x < 32) {
       if (__shfl_sync(0xffffffffu, finished, 0))
-        retire((QpDev*)__shfl_sync(0xffffffffu, (unsigned long long)work.qp, 0), threadIdx.x);
+        retire((QpDev*)__shfl_sync(0xffffffffu, (unsigned long long)work.qp, 0), threadIdx.x, work.w);
     }
   }
   if (threadIdx.x == 0) {

@@ -770,6 +770,11 @@ RN_API int rn_engine_start(void* hca, int n_ctas, uint64_t idle_timeout_ms, uint
   c.stop = h->h_stop; c.qps = h->d_qptab; c.n_qps = nq; c.max_qps = h->max_qps;
   c.idle_timeout_ns = h->idle_timeout_ns; c.rnr_timeout_ns = h->rnr_timeout_ns;
   c.oneshot = h->oneshot;
+  {
+    const char* e = getenv("RN_ENGINE_STORES_IN_FLIGHT");
+    int v = e ? atoi(e) : 0;
+    c.stores_in_flight = (v == 4 || v == 6 || v == 8) ? (unsigned)v : 4u;
+  }
   int rc = push(h, h->d_ctl, &c, sizeof c);
   if (rc) return rc;
   size_t smem = eng::engine_smem_bytes();

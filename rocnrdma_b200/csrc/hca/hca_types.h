@@ -121,8 +121,7 @@ struct QpDev {
   unsigned long long parse_seq;    // ordered-commit turn: WQE index allowed to commit; bit 63 = QP already in error
   unsigned long long offer;        // oldest WQE index that may still have undrawn chunks (helpers go oldest-first)
   unsigned long long retire_head;  // next WQE index to retire in order
-  unsigned int retire_lock;
-  unsigned int pad0;
+  unsigned long long retire_word;  // (retire_head << 1) | locked: ONE compare-and-swap both takes the retire lock and proves whose turn it is
   unsigned long long rq_head;      // next receive WQE of the *peer* to consume
   unsigned long long rq_cached_pi; // responder receive-producer count as last read (a remote read: refreshed only when exhausted)
   // ---- counters (readable from the host; SURVEY.md section 5 "metrics")
@@ -144,7 +143,7 @@ struct EngineCtl {
   unsigned int exited_idle;        // set when the watchdog ended the engine
   unsigned int fatal;              // a DMA never completed; engine bailed out
   unsigned int quit_all;           // the host-doorbell watcher found the engine idle / drained: everybody leaves
-  unsigned int pad;
+  unsigned int stores_in_flight;   // smem ring split: this many TMA stores may still be reading smem, the rest of the ring holds loads (4, 6 or 8)
   unsigned int oneshot;            // exit as soon as every queue is drained (profiling under ncu: kernels are serialised there)
   unsigned long long n_bulk_chunks;     // chunks moved through the TMA bulk path
   unsigned long long t_start, t_exit;   // %globaltimer of engine start / exit (CTA 0)

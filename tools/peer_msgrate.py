@@ -24,7 +24,8 @@ for op, name in [(W.OP_RDMA_WRITE, "write"), (W.OP_RDMA_WRITE_IMM, "write_imm")]
             iters = 256
             if op == W.OP_RDMA_WRITE_IMM:
                 for _ in range(iters): qb.post_recv(md, 0)
-            r = ops.rdma_stream(qa, op, ms, md, size, iters=iters, window=window, slot_stride=max(size, 64), nslots=32, timeout_ms=3000)
+            r = ops.rdma_stream(qa, op, ms, md, size, iters=iters, window=window, burst=max(1, window // 4), signal_every=max(1, window // 4),
+                                slot_stride=max(size, 64), nslots=32, timeout_ms=3000)
             tr = [t for t in qa.read_trace(256) if t["post"] and t["seen"] >= t["post"]]
             seg = lambda a, b: round(st.median([(t[b] - t[a]) / 1e3 for t in tr]), 2) if tr else None
             row = dict(status=r.status, us_per_msg=round(r.us_per_msg, 2), post_to_claim=seg("post", "claim"), claim_to_parsed=seg("claim", "parsed"),

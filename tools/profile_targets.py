@@ -42,6 +42,8 @@ elif what == "engine":
     ops.fill_random(src, 5)
     ms, md = ctx.reg_mr(src), ctx.reg_mr(dst)
     qp = ctx.loopback_qp(depth=16, mem=W.MEM_HOST_PINNED if len(sys.argv) > 2 and sys.argv[2] == 'host' else W.MEM_DEVICE)
+    if os.environ.get("RN_TRACE"):
+        qp.set_flags(trace=True)
     torch.cuda.synchronize()
     for rep in range(2):
         for i in range(4):
@@ -50,4 +52,10 @@ elif what == "engine":
         ctx.engine_run_oneshot(ctas=128)
         wcs = qp.scq.wait(4)
         assert not any(w.is_error for w in wcs)
+        st = ctx.engine_stats()
+        if os.environ.get("RN_TRACE"):
+            for t in qp.read_trace(8):
+                if t["claim"]:
+                    print({k: round((v - st["t_start"]) / 1e3, 1) for k, v in t.items() if k in ("claim", "parsed", "copied", "cqe") and v})
+        print("oneshot device time", (st["t_exit"] - st["t_start"]) / 1e3, "us", round(4 * msg / max(st["t_exit"] - st["t_start"], 1), 1), "GB/s")
     print("engine oneshot ok", ops.compare(src, dst) == 0)
