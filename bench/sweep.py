@@ -49,6 +49,7 @@ def main():
     ms, md, mha, mhb = ctx.reg_mr(src), ctx.reg_mr(dst), ctx.reg_mr(ha), ctx.reg_mr(hb)
     qd = ctx.loopback_qp(depth=256)                                   # device rings: GPU-posted
     qh = ctx.loopback_qp(depth=256, mem=W.MEM_HOST_PINNED)            # host rings: host-posted
+    qmulti = [qd] + [ctx.loopback_qp(depth=256) for _ in range(7)]    # 8 QPs, one posting warp each: message-rate scaling
     torch.cuda.synchronize()
     ctx.engine_start(ctas=a.engine_ctas, idle_timeout_ms=10000)
     rows = []
@@ -68,6 +69,14 @@ def main():
                 ops.rdma_stream(qd, op, l, r, size, iters=min(iters, 128), **kw)
                 res = ops.rdma_stream(qd, op, l, r, size, iters=iters, timeout_ms=5000, **kw)
                 row[name] = {"ok": res.ok, "gbps": round(res.gbps, 3), "us_per_msg": round(res.us_per_msg, 3)}
+            if size <= (4 << 20):
+                # 8 QPs x (post_list 16, cq-mod 16, 128 outstanding); QP q works on its own 1/8 of the pool
+                per = pool // 8
+                kw = dict(window=128, burst=16, signal_every=16, slot_stride=size, nslots=max(1, min(per // size, 512)), stride=per)
+                ops.rdma_stream(qmulti, W.OP_RDMA_WRITE, ms, md, size, iters=min(iters, 128), **kw)
+                res = ops.rdma_stream(qmulti, W.OP_RDMA_WRITE, ms, md, size, iters=iters, timeout_ms=5000, **kw)
+                row["gpu_posted_burst_8qp"] = {"ok": res.ok, "gbps": round(res.gbps, 3), "us_per_msg": round(res.device_ns / 1e3 / max(sum(res.done), 1), 4),
+                                               "mmsgs_per_s": round(sum(res.done) / max(res.device_ns, 1) * 1e3, 2)}
             lat = ops.rdma_stream(qd, W.OP_RDMA_WRITE, ms, md, size, iters=min(iters, 64), window=1, slot_stride=size, nslots=nslots)
             row["gpu_posted"]["latency_us"] = round(lat.us_per_msg, 2)
             ns, err = C.c_uint64(), C.c_uint32()
