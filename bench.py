@@ -178,6 +178,16 @@ def main():
         ops.rdma_stream(qp, W.OP_RDMA_WRITE, mr_slot[0], md_slot[0], 64, iters=32, window=1, stream=stream)
         lat = ops.rdma_stream(qp, W.OP_RDMA_WRITE, mr_slot[0], md_slot[0], 64, iters=128, window=1, stream=stream)
         extras["small_msg"] = {"4KiB_w16_us_per_msg": round(sm.us_per_msg, 2), "64B_latency_us": round(lat.us_per_msg, 2)}
+        try:
+            # perftest-style posting (--post_list / --cq-mod), clamped by the poster to what this QP's window allows
+            bkw = dict(window=32, burst=8, signal_every=8, stream=stream)
+            ops.rdma_stream(qp, W.OP_RDMA_WRITE, mr_slot[0], md_slot[0], 4096, iters=64, slot_stride=4096, nslots=64, **bkw)
+            bm = ops.rdma_stream(qp, W.OP_RDMA_WRITE, mr_slot[0], md_slot[0], 4096, iters=2048, slot_stride=4096, nslots=64, **bkw)
+            mb = ops.rdma_stream(qp, W.OP_RDMA_WRITE, mr_slot[0], md_slot[0], 1 << 20, iters=1024, slot_stride=1 << 20, nslots=64, **bkw)
+            extras["small_msg"].update({"4KiB_burst8_us_per_msg": round(bm.us_per_msg, 3), "1MiB_burst8_gbps": round(mb.gbps, 1),
+                                        "burst_ok": bool(bm.ok and mb.ok)})
+        except Exception as e:  # extras never take the headline down
+            extras["small_msg"]["burst_error"] = str(e)[:120]
     ctx.engine_stop()
     counters = qp.counters()
     torch.cuda.synchronize()

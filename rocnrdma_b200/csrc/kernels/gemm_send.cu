@@ -41,7 +41,7 @@ constexpr int kEpiThreads = 128;
 constexpr uint32_t kTmemCols = 512;                                // two 256-column accumulators
 constexpr unsigned long long kWaitNs = 2000000000ull;
 constexpr int kStageC = 32 * 128;                                  // one TMA-store box: 32 rows x 64 bf16, SWIZZLE_128B
-constexpr uint32_t kFlagDirect = 1, kFlagPlainStores = 2;
+constexpr uint32_t kFlagDirect = 1, kFlagPlainStores = 2, kFlagDenseProbe = 4;
 
 struct alignas(1024) Smem {
   uint8_t a[STAGES][A_STAGE];
@@ -62,6 +62,7 @@ struct GemmArgs {
   uint32_t signal_every;
   uint32_t with_imm;         // 1: RDMA_WRITE_IMM, immediate = panel index (wakes a consumer on the receiving GPU)
   uint32_t out_fp8;          // 1: epilogue emits block-scaled fp8 panel records instead of bf16 rows (see below)
+  uint32_t dense_probe;      // link probe ONLY (output layout is wrong on purpose): every 32x64 box lands as one contiguous 4 KiB run
   uint32_t plain_stores;     // 1: bf16 epilogue writes rows with per-thread 16-byte stores instead of staged TMA stores (A/B switch)
   uint32_t direct;           // 1: `c` IS the peer's registered buffer (NVLink-mapped): the epilogue's stores are the transfer;
                              //    each finished panel is announced by a zero-length RDMA_WRITE_IMM posted after a cumulative
@@ -176,7 +177,8 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-__device__ __forceinline__ void epilogue_rows_tma(uint8_t (*stage)[kStageC], const CUtensorMap* mc, uint32_t taddr, int col0, int row0, int lane) {
+__device__ __forceinline__ void epilogue_rows_tma(uint8_t (*stage)[kStageC], const CUtensorMap* mc, uint32_t taddr, int col0, int row0, int lane,
+                                                  uint32_t dense_n = 0) {
 #pragma unroll 1
   for (int c = 0; c < BN / 64; ++c) {
     const uint32_t buf = s32(stage[c & 1]);
@@ -193,7 +195,11 @@ __device__ __forceinline__ void epilogue_rows_tma(uint8_t (*stage)[kStageC], con
                    pack_bf16(r[8 * j + 4], r[8 * j + 5]), pack_bf16(r[8 * j + 6], r[8 * j + 7]));
     fence_async_smem();                                // my generic-proxy writes -> visible to the async proxy
     __syncwarp();
-    if (lane == 0) { tma_store_2d(mc, stage[c & 1], col0 + c * 64, row0); bulk_commit(); }
+    if (lane == 0) {
+      if (dense_n) tma_store_2d(mc, stage[c & 1], 0, (int)(((uint32_t)row0 / 32u * (dense_n / 64u) + (uint32_t)(col0 + c * 64) / 64u) * 32u));
+      else tma_store_2d(mc, stage[c & 1], col0 + c * 64, row0);
+      bulk_commit();
+    }
   }
 }
 
@@ -335,7 +341,7 @@ gemm_send_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const uint32_t row = m_blk * BM + row_in_panel;
       const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * BN;
       if (!g.out_fp8 && !g.plain_stores) {
-        epilogue_rows_tma(s.stage_c[q], &tmap_c, taddr, (int)(n_blk * BN), (int)(m_blk * BM + q * 32), lane);
+        epilogue_rows_tma(s.stage_c[q], &tmap_c, taddr, (int)(n_blk * BN), (int)(m_blk * BM + q * 32), lane, g.dense_probe ? g.N : 0u);
       } else if (!g.out_fp8) {
         __nv_bfloat16* crow = g.c + (size_t)row * g.N + (size_t)n_blk * BN;
 #pragma unroll 2
@@ -584,7 +590,7 @@ gemm_send2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const uint32_t row = m_blk * BM + row_in_panel;
       const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * BN;
       if (!g.out_fp8 && !g.plain_stores) {
-        epilogue_rows_tma(s.stage_c[q], &tmap_c, taddr, (int)(n_blk * BN), (int)(m_blk * BM + q * 32), lane);
+        epilogue_rows_tma(s.stage_c[q], &tmap_c, taddr, (int)(n_blk * BN), (int)(m_blk * BM + q * 32), lane, g.dense_probe ? g.N : 0u);
       } else if (!g.out_fp8) {
         __nv_bfloat16* crow = g.c + (size_t)row * g.N + (size_t)n_blk * BN;
 #pragma unroll 2
@@ -719,12 +725,13 @@ RN_API int rn_k_gemm_send(uint64_t stream, int grid, uint64_t a, uint64_t b, uin
   CUtensorMap ma, mb, mc;
   int rc = make_map(&ma, (const void*)a, M, K, BM);
   if (!rc) rc = make_map(&mb, (const void*)b, N, K, BN);
-  if (!rc) rc = make_map(&mc, (const void*)c, M, N, 32);           // only dereferenced by the bf16 TMA-store epilogue
+  if (!rc) rc = (flags & kFlagDenseProbe) ? make_map(&mc, (const void*)c, (uint64_t)M * N / 64, 64, 32)
+                                          : make_map(&mc, (const void*)c, M, N, 32);           // only dereferenced by the bf16 TMA-store epilogue
   if (rc) return rc;
   GemmArgs g;
   g.c = (__nv_bfloat16*)c; g.M = M; g.N = N; g.K = K; g.qp = (QpDev*)qp_dev; g.c_va = c_va; g.lkey = lkey; g.rkey = rkey;
   g.remote_va = remote_va; g.signal_every = signal_every ? signal_every : 1; g.with_imm = with_imm; g.out_fp8 = out_fp8; g.group_m = group_m ? group_m : 1;
-  g.direct = (flags & kFlagDirect) ? 1 : 0; g.plain_stores = (flags & kFlagPlainStores) ? 1 : 0;
+  g.direct = (flags & kFlagDirect) ? 1 : 0; g.plain_stores = (flags & kFlagPlainStores) ? 1 : 0; g.dense_probe = (flags & kFlagDenseProbe) ? 1 : 0;
   const uint32_t m_blks = M / BM;
   g.counters = (unsigned int*)counters_dev;
   g.acc = (unsigned long long*)(counters_dev + (((uint64_t)m_blks + 1) * 4 + 7) / 8 * 8);

@@ -95,6 +95,18 @@ __global__ void __launch_bounds__(32, 1) rdma_stream_kernel(StreamArgs a) {
   out[7] = 0;
 }
 
+// Posting parameters that can always make progress (pure host function, unit-tested on the CPU):
+// burst in 1..32 and at most half the window; the window wait targets a WQE `window - burst` behind the
+// newest one, so a signaled WQE must already sit at or after it: signal_every <= window - burst + 1.
+RN_API void rn_stream_clamp(uint32_t window, uint32_t* burst, uint32_t* signal_every) {
+  uint32_t b = *burst ? (*burst > 32 ? 32 : *burst) : 1, s = *signal_every ? *signal_every : 1;
+  if (window) {
+    if (b > (window + 1) / 2) b = (window + 1) / 2;
+    if (s > window - b + 1) s = window - b + 1;
+  }
+  *burst = b; *signal_every = s;
+}
+
 RN_API int rn_k_rdma_stream(uint64_t stream, const uint64_t* qps_host, uint32_t nqp, uint32_t opcode, uint64_t laddr,
                             uint32_t lkey, uint64_t raddr, uint32_t rkey, uint64_t stride, uint32_t bytes,
                             uint32_t iters, uint32_t window, uint32_t signal_every, uint32_t burst, uint64_t slot_stride,
@@ -104,13 +116,8 @@ RN_API int rn_k_rdma_stream(uint64_t stream, const uint64_t* qps_host, uint32_t 
   for (uint32_t i = 0; i < nqp; ++i) a.qps[i] = (QpDev*)qps_host[i];
   a.opcode = opcode; a.laddr = laddr; a.raddr = raddr; a.stride = stride;
   a.lkey = lkey; a.rkey = rkey; a.bytes = bytes; a.iters = iters; a.window = window;
-  a.signal_every = signal_every ? signal_every : 1;
-  a.burst = burst ? (burst > 32 ? 32 : burst) : 1;
-  if (window) {
-    // the window wait targets a WQE `window - n` behind the newest: a signaled one must already sit at or after it
-    if (a.burst > (window + 1) / 2) a.burst = (window + 1) / 2;
-    if (a.signal_every > window - a.burst + 1) a.signal_every = window - a.burst + 1;
-  }
+  rn_stream_clamp(window, &burst, &signal_every);
+  a.signal_every = signal_every; a.burst = burst;
   a.slot_stride = slot_stride; a.nslots = nslots ? nslots : 1;
   a.timeout_ns = (timeout_ms ? timeout_ms : 2000) * 1000000ull;
   a.out = (unsigned long long*)out_dev;

@@ -37,7 +37,13 @@ def run(M: int = 8192, N: int = 8192, K: int = 2048, engine_ctas: int = 0, gpus=
         mode: str = "engine") -> SendRecvResult:
     """mode="engine": panels are staged in GPU0's send buffer and moved by the DMA engine (RDMA semantics).
     mode="direct": the GEMM epilogue stores straight into GPU1's registered buffer over NVLink and only the
-    per-panel completion signal (zero-length RDMA_WRITE_IMM) goes through the queue pair."""
+    per-panel completion signal (zero-length RDMA_WRITE_IMM) goes through the queue pair.
+    mode="auto": direct for compute-heavy shapes (K >= 4096), engine otherwise."""
+    if mode == "auto":
+        # direct stores top out near 450 GB/s (bursty: all CTAs reach their epilogue together and only one TMEM
+        # buffer of slack absorbs it), the engine streams at NVLink rate but costs 32 SMs: measured crossover
+        # is where a tile's compute time covers its 64 KiB leaving the SM at that rate, about K >= 4096
+        mode = "direct" if K >= 4096 else "engine"
     g0, g1 = gpus
     d0, d1 = torch.device("cuda", g0), torch.device("cuda", g1)
     tx, rx = Context(g0), Context(g1)

@@ -1,6 +1,8 @@
 """K4 wrapper: tcgen05/TMEM/TMA bf16 GEMM whose epilogue RDMA-writes finished 128-row panels."""
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from dataclasses import dataclass
 
@@ -113,7 +115,7 @@ def gemm_send(ctx, a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, c_mr=None,
     rc = lib.rn_k_gemm_send(_stream_ptr(ws), grid, a.data_ptr(), b.data_ptr(), c.data_ptr(), M, Nn, K,
                             qp.dev_ptr if qp is not None else 0, c_mr.addr if c_mr is not None else 0,
                             c_mr.lkey if c_mr is not None else 0, dst_mr.addr if dst_mr is not None else 0,
-                            dst_mr.rkey if dst_mr is not None else 0, signal_every, int(with_imm), int(out_fp8), cta_group, group_m, int(direct) | (2 if plain_stores else 0), counters, out_addr, timeout_ms)
+                            dst_mr.rkey if dst_mr is not None else 0, signal_every, int(with_imm), int(out_fp8), cta_group, group_m, int(direct) | (2 if plain_stores else 0) | (4 if os.environ.get("RN_GEMM_DENSE_PROBE") else 0), counters, out_addr, timeout_ms)
     if rc:
         raise N.NativeError(f"gemm_send launch failed ({rc})")
     if not sync:

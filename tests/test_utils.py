@@ -46,3 +46,22 @@ def test_pack_and_gemm_record_geometry():
     from rocnrdma_b200.ops import gemm, pack
     assert pack.record_bytes(1 << 22) == (1 << 22) + (1 << 17)
     assert gemm.panel_record_bytes(8192) == 128 * 8192 * 33 // 32
+
+
+def test_stream_posting_parameters_always_allow_progress():
+    """Device poster: burst / cq-moderation are clamped so the window wait always has a signaled WQE to wait for."""
+    import ctypes as C
+    from rocnrdma_b200 import _native as N
+    lib = N.load()
+    for window in (0, 1, 2, 3, 8, 16, 33, 128):
+        for burst in (0, 1, 7, 16, 32, 500):
+            for sig in (0, 1, 4, 16, 100, 1000):
+                b, s = C.c_uint32(burst), C.c_uint32(sig)
+                lib.rn_stream_clamp(window, C.byref(b), C.byref(s))
+                assert 1 <= b.value <= 32 and s.value >= 1
+                if window:
+                    assert b.value <= (window + 1) // 2
+                    # newest signaled WQE is at most s-1 behind the newest posted; the wait target is window-b behind
+                    assert s.value - 1 <= window - b.value
+                else:
+                    assert b.value == min(max(burst, 1), 32) and s.value == max(sig, 1)
