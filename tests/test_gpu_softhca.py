@@ -245,3 +245,80 @@ def test_device_preposted_receives_and_gpu_posted_sends(ctx):
     cons = ops.parse_recv(view)
     assert r.ok and cons["status"] == "OK" and cons["seen"] == k and cons["bytes"] == n * k, (r, cons)
     assert torch.equal(src, dst)
+
+
+def test_batch_claim_error_in_the_middle_flushes_the_rest(ctx):
+    """16 WQEs are visible when the engine starts, so one CAS claims them as a batch and a warp parses them:
+    WQE 5 names a region without REMOTE_WRITE -> 0..4 complete, 5 fails with the IB syndrome, 6..15 are flushed
+    in order, nothing of 5..15 moves."""
+    n = 4096
+    src, dst = _bufs(16 * n)
+    bad = torch.zeros(n, dtype=torch.uint8, device="cuda:0")
+    ms, md = ctx.reg_mr(src), ctx.reg_mr(dst)
+    mbad = ctx.reg_mr(bad, access=W.ACC_LOCAL_WRITE)
+    qp = ctx.loopback_qp(depth=32)
+    for i in range(16):
+        if i == 5:
+            qp.post_write(ms, mbad, n, src_off=i * n)
+        else:
+            qp.post_write(ms, md, n, src_off=i * n, dst_off=i * n)
+    torch.cuda.synchronize()
+    ctx.engine_run_oneshot(ctas=8)
+    wcs = qp.scq.wait(16)
+    assert [w.wqe_counter for w in wcs] == list(range(16))
+    assert not any(w.is_error for w in wcs[:5])
+    assert wcs[5].is_error and wcs[5].status == "REMOTE_ACCESS_ERR"
+    assert all(w.is_error and w.status == "WR_FLUSH_ERR" for w in wcs[6:])
+    assert qp.state == "ERR"
+    assert torch.equal(dst[:5 * n], src[:5 * n]) and int(dst[5 * n:].sum()) == 0 and int(bad.sum()) == 0
+    c = qp.counters()
+    assert c["n_wqe"] == 16 and c["n_err"] == 11 and c["cursor"] == 16 and c["retire_head"] == 16
+
+
+def test_burst_sends_match_receives_in_order(ctx):
+    """Burst-posted SENDs go through the batch path; receive matching stays strictly in order."""
+    n, k = 2048, 64
+    src, dst = _bufs(n * k)
+    ms, md = ctx.reg_mr(src), ctx.reg_mr(dst)
+    cq_a, cq_b = ctx.create_cq(256), ctx.create_cq(256, W.MEM_HOST_PINNED)
+    qa = ctx.create_qp(cq_a, cq_a, 128, 16)
+    qb = ctx.create_qp(cq_b, cq_b, 16, 128, W.MEM_HOST_PINNED)
+    qa.connect(qb)
+    for i in range(k):
+        qb.post_recv(md, n, off=i * n)
+    torch.cuda.synchronize()
+    ctx.engine_start(ctas=8, idle_timeout_ms=3000)
+    try:
+        r = ops.rdma_stream(qa, W.OP_SEND, ms, None, n, iters=k, window=64, burst=16, signal_every=16, slot_stride=n, nslots=k)
+        wcs = cq_b.wait(k)
+    finally:
+        ctx.engine_stop()
+    assert r.ok and r.done == [k]
+    assert [w.wqe_counter for w in wcs] == list(range(k))
+    assert all(w.opcode == W.CQE_RESP_SEND and w.byte_cnt == n for w in wcs)
+    assert torch.equal(src, dst)
+    assert qa.counters()["n_cqe"] == k // 16          # cq moderation: one send CQE per 16 WQEs
+
+
+@pytest.mark.parametrize("nbytes", [64, 4096, 262144])
+def test_burst_stream_many_qps_soak(ctx, nbytes):
+    """8 QPs x 2048 burst-posted writes each: batch claims, warp retirement and the ticket spread all busy at once."""
+    nq, iters = 8, 2048
+    nslots = min(256, (32 << 20) // nbytes)
+    per = nslots * nbytes
+    src, dst = _bufs(nq * per)
+    ms, md = ctx.reg_mr(src), ctx.reg_mr(dst)
+    qps = [ctx.loopback_qp(depth=256) for _ in range(nq)]
+    torch.cuda.synchronize()
+    ctx.engine_start(ctas=48, idle_timeout_ms=3000)
+    try:
+        r = ops.rdma_stream(qps, W.OP_RDMA_WRITE, ms, md, nbytes, iters=iters, window=128, burst=16, signal_every=16,
+                            slot_stride=nbytes, nslots=nslots, stride=per, timeout_ms=5000)
+    finally:
+        ctx.engine_stop()
+    assert r.ok and r.done == [iters] * nq, r
+    assert ops.compare(src, dst) == 0
+    for q in qps:
+        c = q.counters()
+        assert c["n_wqe"] == iters and c["n_err"] == 0 and c["n_db_order_violations"] == 0
+        assert c["n_cqe"] == iters // 16 and c["n_bytes"] == iters * nbytes
