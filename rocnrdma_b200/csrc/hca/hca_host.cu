@@ -378,7 +378,7 @@ static int mr_lookup(Hca* h, uint32_t key, uint32_t* idx) {
 RN_API int rn_mr_revoke(void* hca, uint32_t key) {
   Hca* h = (Hca*)hca;
   std::lock_guard<std::mutex> g(h->mu);
-  uint32_t i;
+  uint32_t i = 0;
   int rc = mr_lookup(h, key, &i);
   if (rc) return rc;
   if (h->mrs[i].state == MR_REVOKED) return 0;
@@ -393,7 +393,7 @@ RN_API int rn_mr_revoke(void* hca, uint32_t key) {
 RN_API int rn_dereg_mr(void* hca, uint32_t key) {
   Hca* h = (Hca*)hca;
   std::lock_guard<std::mutex> g(h->mu);
-  uint32_t i;
+  uint32_t i = 0;
   int rc = mr_lookup(h, key, &i);
   if (rc) return rc;
   Mr& m = h->mrs[i];

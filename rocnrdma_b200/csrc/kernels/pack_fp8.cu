@@ -117,8 +117,6 @@ __global__ void __launch_bounds__(kPackThreads) pack_fp8_write_kernel(PackArgs a
   const uint64_t n_groups = n_tiles / G;
   const uint32_t groups_per_chunk = tiles_per_chunk / G;
   const bool sys = a.qp != nullptr && poster_sys(a.qp);
-  __shared__ int posted_here;
-  if (threadIdx.x == 0) posted_here = 0;
   for (uint64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
     const uint64_t first_tile = grp * G;
     const uint32_t chunk = (uint32_t)(first_tile / tiles_per_chunk);
@@ -147,7 +145,6 @@ __global__ void __launch_bounds__(kPackThreads) pack_fp8_write_kernel(PackArgs a
             atomicMax(&a.acc[0], idx + 1);
             atomicAdd(&a.acc[1], 1ull);
             atomicMax(&a.acc[2], ~globaltimer_ns());
-            posted_here = 1;
           } else {
             a.out[0] = (unsigned long long)(long long)WAIT_TIMEOUT;
           }
