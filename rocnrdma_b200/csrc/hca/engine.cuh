@@ -680,7 +680,7 @@ __global__ void __launch_bounds__(kThreads, 1) engine_kernel(EngineCtl* ctl) {
   // touches device memory, so everybody still does that.
   const bool host_watcher = blockIdx.x == gridDim.x - 1;
   uint32_t n_qps_cached = ctl->n_qps;
-  unsigned iter = 0;
+  unsigned iter = 0, rot = blockIdx.x;
   for (;;) {
     int batch_k = 0;
     if (threadIdx.x == 0) {
@@ -698,14 +698,22 @@ __global__ void __launch_bounds__(kThreads, 1) engine_kernel(EngineCtl* ctl) {
         if (draw_chunk(sticky_qp, sr, sticky_w, &work)) s.have_work = 1;
         else sticky_qp = nullptr;
       }
-      for (uint32_t k = 0; k < n && !s.have_work && !batch_k; ++k) {
-        QpDev* qp = *(QpDev* volatile*)&ctl->qps[(rr + k) % n];   // table grows while we run
+      // Every probe of a QP is at least one L2 round trip, so a CTA does not walk the whole table each
+      // iteration (with 8 QPs registered, one active QP ran at half its solo message rate): it looks at the QP
+      // that last gave it work and at ONE other, rotating.  CTAs start at different offsets, so every QP is
+      // still probed by many CTAs per round trip.  The host watcher keeps the full scan: it alone decides
+      // "idle" / "drained" and it is the only one that reads host-resident doorbells.
+      const uint32_t n_scan = host_watcher ? n : (n < 2 ? n : 2u);
+      for (uint32_t k = 0; k < n_scan && !s.have_work && !batch_k; ++k) {
+        const uint32_t qi = (host_watcher || k == 0) ? (rr + k) % n : (rr + 1 + rot % (n - 1)) % n;
+        QpDev* qp = *(QpDev* volatile*)&ctl->qps[qi];   // table grows while we run
         if (!qp) continue;
         const int got = try_claim(ctl, qp, &work, &pending, host_watcher);
         if (got == 1) s.have_work = 1;
         else if (got == 2) { batch_k = (int)work.chunk; pending = true; }
-        if (got) rr = (rr + k) % n;
+        if (got) rr = qi;
       }
+      ++rot;
       if (s.have_work) {
         if (work.have_desc) {
           s.len = work.len; s.src = work.src; s.dst = work.dst; s.nch = work.nch;
