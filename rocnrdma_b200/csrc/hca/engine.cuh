@@ -1,7 +1,8 @@
 // The softhca DMA engine: a persistent sm_100a kernel that plays the HCA.
 //
 // Pipeline per QP (every stage can be on a different CTA, many WQEs in flight):
-//   claim    one CAS on the claim head hands WQE w to a CTA (the doorbell bounds it)
+//   claim    one CAS on the claim head hands WQE w -- or, with a backlog visible, up to 16 WQEs -- to a
+//            CTA (the doorbell bounds it)
 //   parse    that CTA reads + decodes the WQE and translates both MKeys -- in parallel
 //            with the CTAs parsing w-1, w+1, ...
 //   commit   a short ordered section (parse_seq turn): QP-error flush, receive-WQE
@@ -9,7 +10,8 @@
 //   move     TMA bulk-copy pipeline (cp.async.bulk global->shared->global, one issuing
 //            thread, mbarrier-tracked, no LSU traffic); a multi-chunk WQE is offered to
 //            idle CTAs through a fetch-add ticket, its owner keeps drawing from it too
-//   retire   strictly in order: mlx5 CQEs are written under a per-QP retire lock
+//   retire   strictly in order, warp-collective: one CAS on retire_word = (head << 1) | locked takes the
+//            per-QP lock and proves the turn, lane i publishes the mlx5 CQEs of WQE head + i
 // Large transfers fan out over every engine CTA (HBM / NVLink speed); small messages
 // cost one claim + one ordered hand-off each and pipeline across CTAs.
 //
@@ -35,7 +37,8 @@ using namespace rn::dev;
 constexpr int kThreads = 128;
 constexpr uint32_t kSub = 16384;        // bytes per TMA bulk transaction
 constexpr int kStages = 12;             // smem ring: 12 x 16 KiB
-constexpr int kStoresInFlight = 4;      // stages whose TMA store may still be reading smem; the other 8 hold loads in flight
+// ring split: EngineCtl::stores_in_flight stages (default 4) may hold a TMA store that is still reading smem,
+// the others hold loads in flight (copy_bulk<kSif>)
 constexpr uint32_t kBulkMin = 4096;     // below this the generic path is as fast
 
 // ------------------------------------------------------------------ PTX helpers
@@ -151,7 +154,7 @@ struct Smem {
   uint32_t phase_bits;   // per-stage parity of the next wait
 };
 
-// Bulk path: thread 0 keeps kStages-kStoresInFlight loads and kStoresInFlight stores in flight.
+// Bulk path: thread 0 keeps kStages - kSif loads and kSif stores in flight.
 // (With a single store in flight every 16 KiB step exposed the store's smem-read latency,
 // ~0.35 us, which capped a CTA near 45 GB/s.)  Requires 16-byte aligned src, dst and len.
 template <int kSif>
@@ -179,8 +182,8 @@ __device__ __forceinline__ bool copy_bulk(Smem& s, uint64_t src, uint64_t dst, u
     bulk_s2g((void*)(dst + (uint64_t)i * kSub), s.ring[st], sub_len(i));
     bulk_commit();
     if (issued < nsub) {
-      // the stage of load `issued` (= i + P) was last read by store i - kStoresInFlight:
-      // stores i .. i-kStoresInFlight+1 may still be pending
+      // the stage of load `issued` (= i + P) was last read by store i - kSif:
+      // stores i .. i - kSif + 1 may still be pending
       bulk_wait_read<kSif>();
       int ls = issued % kStages;
       mbar_expect_tx(&s.full[ls], sub_len(issued));
