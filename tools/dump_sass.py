@@ -17,7 +17,7 @@ for m in re.finditer(r"\t\tFunction : (\S+)\n(.*?)(?=\n\t\tFunction : |\Z)", txt
     ops = collections.Counter()
     full = collections.Counter()
     for line in body.splitlines():
-        mm = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)((?:\.[A-Z0-9_]+)*)", line)
+        mm = re.match(r"\s+/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)((?:\.[A-Z0-9_]+)*)", line)
         if mm:
             ops[mm.group(1)] += 1
             full[mm.group(1) + mm.group(2)] += 1
