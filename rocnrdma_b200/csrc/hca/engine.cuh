@@ -660,9 +660,10 @@ __device__ __forceinline__ void claim_batch(EngineCtl* ctl, QpDev* qp, unsigned 
 __global__ void __launch_bounds__(kThreads, 1) engine_kernel(EngineCtl* ctl) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>(smem_raw);
-  __shared__ Work work;
-  __shared__ int quit;
+  __shared__ Work work, next_work;   // next_work: the following chunk of the same WQE, drawn by a second thread while this one is copied
+  __shared__ int quit, next_valid;
   if (threadIdx.x == 0) {
+    next_valid = 0;
     for (int i = 0; i < kStages; ++i) mbar_init(&s.full[i], 1);
     s.phase_bits = 0;
     quit = 0;
@@ -695,7 +696,11 @@ __global__ void __launch_bounds__(kThreads, 1) engine_kernel(EngineCtl* ctl) {
       if ((iter++ & 63u) == 0) { fence_gpu(); n_qps_cached = ctl->n_qps; }
       const uint32_t n = n_qps_cached;
       bool pending = false;
-      if (sticky_qp) {
+      if (next_valid) {              // drawn (and therefore owed) during the previous chunk's copy
+        work = next_work;
+        next_valid = 0;
+        s.have_work = 1;
+      } else if (sticky_qp) {
         Resolved* sr = sticky_qp->resolved + (sticky_w & ((1u << sticky_qp->sq_log) - 1));
         // a successful draw is a claim that MUST be executed, whichever generation it names
         if (draw_chunk(sticky_qp, sr, sticky_w, &work)) s.have_work = 1;
@@ -767,6 +772,25 @@ __global__ void __launch_bounds__(kThreads, 1) engine_kernel(EngineCtl* ctl) {
     if (!hw) continue;
     if (len > 0) {
       const bool bulk = len >= kBulkMin && (((csrc | cdst) & 15) == 0) && ((len & 15) == 0);
+      if (bulk && threadIdx.x == 32 && s.nch > 1) {
+        // While thread 0 runs the copy pipeline, draw the NEXT chunk of the same WQE and fetch its descriptor:
+        // takes the ticket round trips, the fence and the descriptor loads (~2 us) off the per-chunk path.
+        Work nw;
+        if (draw_chunk(work.qp, work.qp->resolved + (work.w & ((1u << work.qp->sq_log) - 1)), work.w, &nw)) {
+          Resolved* r2 = nw.qp->resolved + (nw.w & ((1u << nw.qp->sq_log) - 1));   // the ticket names its own WQE
+          const uint4 f = ld_v4_volatile(reinterpret_cast<const uint8_t*>(r2) + 16);
+          const uint4 a = ld_v4_volatile(reinterpret_cast<const uint8_t*>(r2));
+          const uint32_t chunk = *(volatile uint32_t*)&r2->chunk;
+          const uint64_t off = (uint64_t)nw.chunk * chunk;
+          nw.have_desc = 1;
+          nw.len = f.x == 0 ? 0 : (uint32_t)((f.x - off < chunk) ? (f.x - off) : chunk);
+          nw.src = (((uint64_t)a.y << 32) | a.x) + off;
+          nw.dst = (((uint64_t)a.w << 32) | a.z) + off;
+          nw.nch = f.y;
+          next_work = nw;
+          next_valid = 1;
+        }
+      }
       if (bulk) {
         if (threadIdx.x == 0) {
           const unsigned sif = ctl->stores_in_flight;

@@ -33,22 +33,28 @@ for (M, N, K) in shapes:
     plain2 = max(ops.gemm_send(ctx, a, b, c, cta_group=2, plain_stores=True).tflops for _ in range(5))
     row = dict(M=M, N=N, K=K, group_m_sweep_2cta=gm, ours_2cta_plain_store_epilogue_tflops=round(plain2, 1), cublas_tflops=round(cublas_tf, 1), ours_1cta_tflops=round(best, 1), frac_1cta=round(best / cublas_tf, 3),
                ours_2cta_tflops=round(best2, 1), frac_2cta=round(best2 / cublas_tf, 3))
-    for ectas in [16]:
+    by_ctas = {}
+    for ectas in [16, 32]:
         ctx.engine_start(ctas=ectas, idle_timeout_ms=3000)
         grid = 148 - ectas
         ops.gemm_send(ctx, a, b, c, c_mr=cm, qp=qp, dst_mr=dm, signal_every=4, grid=grid)
         f = min((ops.gemm_send(ctx, a, b, c, c_mr=cm, qp=qp, dst_mr=dm, signal_every=4, grid=grid) for _ in range(3)), key=lambda r: r.device_ns)
-        # unfused: GEMM (compute only, same grid), then one GPU-posted write of C
-        with torch.cuda.stream(ctx.stream):
-            ev[0].record()
-            ops.gemm_send(ctx, a, b, c, grid=grid, sync=False)
-            ops.rdma_stream(qp, W.OP_RDMA_WRITE, cm, dm, min(2 * M * N, (1 << 31) - 65536), iters=1, sync=False)
-            ev[1].record(); ev[1].synchronize()
-        unf_us = ev[0].elapsed_time(ev[1]) * 1e3
+        # unfused: GEMM (compute only, same grid), then one GPU-posted write of C; best of 3
+        unf_us = 1e30
+        for _ in range(3):
+            with torch.cuda.stream(ctx.stream):
+                ev[0].record()
+                ops.gemm_send(ctx, a, b, c, grid=grid, sync=False)
+                ops.rdma_stream(qp, W.OP_RDMA_WRITE, cm, dm, min(2 * M * N, (1 << 31) - 65536), iters=1, sync=False)
+                ev[1].record(); ev[1].synchronize()
+            unf_us = min(unf_us, ev[0].elapsed_time(ev[1]) * 1e3)
         ctx.engine_stop()
-        row.update(dict(engine_ctas=ectas, fused_ok=f.ok, fused_us=round(f.device_ns / 1e3, 1), fused_tflops=round(f.tflops, 1),
-                        compute_phase_us=round((f.t_compute_end_ns - f.t_start_ns) / 1e3, 1), unfused_us=round(unf_us, 1),
-                        verify=bool(torch.equal(c, d))))
+        by_ctas[ectas] = dict(engine_ctas=ectas, fused_ok=f.ok, fused_us=round(f.device_ns / 1e3, 1), fused_tflops=round(f.tflops, 1),
+                              compute_phase_us=round((f.t_compute_end_ns - f.t_start_ns) / 1e3, 1), unfused_us=round(unf_us, 1),
+                              verify=bool(torch.equal(c, d)))
+    best_e = min(by_ctas, key=lambda e: by_ctas[e]["fused_us"])
+    row.update(by_ctas[best_e])
+    row["fused_by_engine_ctas"] = by_ctas
     rows.append(row); print(row, flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(rows, open("gpurun_out/gemm_bench.json", "w"), indent=1)
