@@ -113,15 +113,19 @@ def connect_to(ctx, qp, peer: PeerInfo) -> Dict[int, RemoteMR]:
     return out
 
 
-def connect_ring(ctx, qp, mrs, group=None):
+def connect_ring(ctx, qp, mrs, group=None, describe=None, connect=None):
     """All ranks call this: rank r's QP is connected to rank (r+1) % world's QP.  Returns
-    (next_rank, {rkey: RemoteMR}) describing what this rank may write to / read from."""
+    (next_rank, {rkey: RemoteMR}) describing what this rank may write to / read from.
+    ``describe`` / ``connect`` default to ``describe_local`` / ``connect_to``; the CPU test of the rendezvous
+    (gloo, two processes) substitutes GPU-free stand-ins."""
     import torch.distributed as dist
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    me = describe_local(ctx, qp, mrs, rank)
+    me = (describe or describe_local)(ctx, qp, mrs, rank)
     infos: List[Optional[PeerInfo]] = [None] * world
     dist.all_gather_object(infos, me, group=group)
     nxt = (rank + 1) % world
-    remote = connect_to(ctx, qp, infos[nxt])
+    if infos[nxt] is None or infos[nxt].rank != nxt:
+        raise RuntimeError(f"rank {rank}: rendezvous returned no description for rank {nxt}")
+    remote = (connect or connect_to)(ctx, qp, infos[nxt])
     dist.barrier(group=group)           # everybody is mapped before anybody starts writing
     return nxt, remote
