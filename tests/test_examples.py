@@ -1,0 +1,22 @@
+"""The README quick start must keep running as written (examples/quickstart.py is generated from it)."""
+import os
+import runpy
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_readme_snippet_and_example_are_the_same_text():
+    readme = open(os.path.join(ROOT, "README.md")).read()
+    i = readme.index("```python\nimport torch, rocnrdma_b200 as rn")
+    code = readme[i + len("```python\n"):readme.index("```", i + 10)]
+    assert code in open(os.path.join(ROOT, "examples", "quickstart.py")).read()
+
+
+def test_quickstart_runs(capsys):
+    runpy.run_path(os.path.join(ROOT, "examples", "quickstart.py"), run_name="__main__")
+    out = capsys.readouterr().out
+    assert "GB/s device-timed" in out and "us per message" in out and "TFLOP/s including delivery" in out
