@@ -201,6 +201,7 @@ class Context:
         self.device = device
         self._mrs: List[MemoryRegion] = []
         self._closed = False
+        self.last_engine_fatal = 0
         self._stream = None
         sz = C.c_uint64()
         self._scratch_ptr = self._lib.rn_hca_scratch(self._h, C.byref(sz))
@@ -329,11 +330,27 @@ class Context:
         try:
             N.check(self._lib.rn_engine_start(self._h, ctas, 2000, 500), "engine_start")
             N.check(self._lib.rn_engine_wait(self._h), "engine_wait")
+            self._report_engine_fault()
         finally:
             self._lib.rn_engine_set_oneshot(self._h, 0)
 
     def engine_stop(self):
         N.check(self._lib.rn_engine_stop(self._h), "engine_stop")
+        self._report_engine_fault()
+
+    def _report_engine_fault(self):
+        """Failure detection: the engine bails out (instead of wedging an SM) when a bulk copy never completes
+        (1) or a CTA that held the commit turn died (2); the host learns it here."""
+        try:
+            fatal = self.engine_stats()["fatal"]
+        except Exception:
+            return
+        self.last_engine_fatal = fatal
+        if fatal:
+            import warnings
+            warnings.warn(f"rocnrdma_b200: the DMA engine stopped after a fatal fault (code {fatal}: "
+                          f"{'a TMA bulk copy never completed (bad mapping?)' if fatal == 1 else 'ordered-commit predecessor lost'}); "
+                          "outstanding work requests were not completed", RuntimeWarning, stacklevel=3)
 
     @property
     def engine_running(self) -> bool:
