@@ -65,3 +65,30 @@ def test_stream_posting_parameters_always_allow_progress():
                     assert s.value - 1 <= window - b.value
                 else:
                     assert b.value == min(max(burst, 1), 32) and s.value == max(sig, 1)
+
+
+def test_fp8_panel_reference_roundtrip_and_record_geometry():
+    """The PyTorch reference of the GEMM's fp8 epilogue (what the GPU test compares the kernel with):
+    record geometry, UE8M0 scales that are the smallest power of two keeping the block within e4m3 range,
+    and a dequantised error bounded by the e4m3 step at each block's scale."""
+    import torch
+    from rocnrdma_b200.ops import gemm as G
+    torch.manual_seed(3)
+    M, Nn = 256, 512
+    c = torch.randn(M, Nn) * torch.logspace(-6, 6, Nn // 32).repeat_interleave(32)[None, :]      # 12 decades of block magnitudes
+    c[5, 64:96] = 0.0                                                                              # an all-zero block
+    rec = G.ref_fp8_panels(c)
+    assert rec.dtype == torch.uint8 and rec.numel() == (M // 128) * G.panel_record_bytes(Nn)
+    assert G.panel_record_bytes(Nn) == 128 * Nn + 128 * (Nn // 32)
+    back = G.dequant_fp8_panels(rec, M, Nn)
+    blocks = c.reshape(M, Nn // 32, 32)
+    amax = blocks.abs().amax(dim=2)
+    r = rec.reshape(M // 128, G.panel_record_bytes(Nn))
+    e = r[:, 128 * Nn:].to(torch.int32).reshape(M, Nn // 32) - 127
+    scale = torch.pow(2.0, e.double())
+    nz = amax > 0
+    assert bool(((amax.double() / scale)[nz] <= 448.0).all())                 # fits e4m3 after scaling ...
+    assert bool(((amax.double() / (scale / 2))[nz] > 448.0).all())            # ... and no smaller power of two would
+    err = (back.reshape(M, Nn // 32, 32) - blocks).abs().double()
+    assert bool((err <= (scale * 32.0)[..., None] * 0.5 + 1e-30).all())       # half of e4m3's largest step (2^5 at 2^8) times the scale
+    assert bool((back.reshape(M, Nn // 32, 32)[5, 2] == 0).all())
