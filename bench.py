@@ -59,6 +59,12 @@ def main():
     if world != args.gpus and world > 1:
         args.gpus = world
     warmup = max(args.warmup, 3)
+    if not torch.cuda.is_available():
+        # the GPU-initiated path has no CPU fallback by design: say so in one line instead of a traceback
+        if rank == 0:
+            print(json.dumps({"metric": "rdma_write_gbps_gpu_hbm_device_timed", "value": None, "impl": "ours",
+                              "unavailable": "no CUDA device visible: the data path is sm_100a kernels only"}))
+        return 2
     torch.cuda.set_device(local_rank)
     from rocnrdma_b200.utils.affinity import bind_to_gpu
     cpus = bind_to_gpu(local_rank)          # pinned buffers get first-touched on the GPU's NUMA node
