@@ -26,6 +26,8 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 def reference_arm():
     # `pip install --no-index ... /root/reference` fails: the reference is a Linux kernel module for
     # AMD KFD + MLNX_OFED 3.2 (no setup.py / pyproject, no userspace, needs amd_rdma.h); see DESIGN.md.
+    if int(os.environ.get("RANK", "0")) != 0:      # launched like our own arm (torchrun for N > 1): one line, from rank 0
+        return 0
     print(json.dumps({"impl": "reference",
                       "unavailable": "reference is an AMD-KFD/MLNX_OFED kernel module (amdp2p.ko): not pip-installable, "
                                      "no userspace entry point, cannot build or load on a B200 box"}))
