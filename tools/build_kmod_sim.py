@@ -1,6 +1,7 @@
 """Build kmod/libb200p2p_sim.so: both kernel modules compiled unchanged against the userspace shim."""
 from __future__ import annotations
 
+import os
 import subprocess
 import sys
 from pathlib import Path
@@ -13,17 +14,30 @@ FLAGS = ["-O1", "-g", "-fPIC", "-fvisibility=hidden", "-Wall", "-Wextra", "-Wno-
 
 
 def build(force: bool = False) -> Path:
+    """RN_KMOD_SIM_SANITIZE=1 builds a SEPARATE library with UBSan (=asan: + AddressSanitizer, the caller preloads
+    libasan): the module sources run their whole simulated life cycle under the sanitizers
+    (`make -C kmod check-sanitize`).  The plain library is never replaced by an instrumented one."""
+    flags, link, lib, tag = list(FLAGS), [], LIB, "sim"
+    mode = os.environ.get("RN_KMOD_SIM_SANITIZE")
+    if mode:
+        san = ["-fsanitize=undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer"]
+        if mode == "asan":
+            san.insert(0, "-fsanitize=address")
+        flags += san
+        link += san
+        tag = "san_asan" if mode == "asan" else "san"
+        lib = KMOD / f"libb200p2p_{tag}.so"
     srcs = [(KMOD / "b200p2p.c", "b200p2p"), (KMOD / "b200p2ptest.c", "b200p2ptest"), (KMOD / "shim" / "sim_runtime.c", "sim")]
     deps = [s for s, _ in srcs] + list((KMOD / "shim").rglob("*.h")) + list((KMOD / "include").glob("*.h"))
-    if not force and LIB.exists() and all(LIB.stat().st_mtime >= d.stat().st_mtime for d in deps):
-        return LIB
+    if not force and lib.exists() and all(lib.stat().st_mtime >= d.stat().st_mtime for d in deps):
+        return lib
     objs = []
     for src, mod in srcs:
-        obj = KMOD / f".{mod}.sim.o"
-        subprocess.run(["gcc", *FLAGS, f"-DKBUILD_MODNAME={mod}", "-c", str(src), "-o", str(obj)], check=True)
+        obj = KMOD / f".{mod}.{tag}.o"
+        subprocess.run(["gcc", *flags, f"-DKBUILD_MODNAME={mod}", "-c", str(src), "-o", str(obj)], check=True)
         objs.append(str(obj))
-    subprocess.run(["gcc", "-shared", "-o", str(LIB), *objs, "-lpthread"], check=True)
-    return LIB
+    subprocess.run(["gcc", "-shared", "-o", str(lib), *objs, *link, "-lpthread"], check=True)
+    return lib
 
 
 if __name__ == "__main__":
