@@ -53,6 +53,7 @@ class WorkCompletion:
 
 
 class MemoryRegion:
+    """A registered range (what ``ibv_reg_mr`` returns): ``addr``/``length``, one key used as lkey and rkey (mlx5 style), access bits; ``state`` follows PINNED -> REVOKED -> FREE."""
     def __init__(self, ctx: "Context", addr: int, length: int, key: int, access: int, keepalive=None):
         self.ctx, self.addr, self.length, self.key, self.access = ctx, addr, length, key, access
         self.lkey = self.rkey = key
@@ -61,6 +62,7 @@ class MemoryRegion:
 
     @property
     def state(self) -> str:
+        """FREE / PINNED / REVOKED, read from the HCA."""
         return ["FREE", "PINNED", "REVOKED"][self.ctx._lib.rn_mr_state(self.ctx._h, self.key)]
 
     def revoke(self):
@@ -69,6 +71,7 @@ class MemoryRegion:
         N.check(self.ctx._lib.rn_mr_revoke(self.ctx._h, self.key), "mr_revoke")
 
     def dereg(self):
+        """Release the MKey slot (and the dma-buf pin, if any).  Safe after ``revoke``."""
         if self._live:
             N.check(self.ctx._lib.rn_dereg_mr(self.ctx._h, self.key), "dereg_mr")
             self._live = False
@@ -79,6 +82,7 @@ class MemoryRegion:
 
 
 class CompletionQueue:
+    """A completion queue: 64-byte mlx5 CQEs with an owner bit, in device or pinned host memory.  Device posters poll it themselves; these methods are the host-side consumer."""
     def __init__(self, ctx, handle, depth, mem):
         self.ctx, self._c, self.depth, self.mem = ctx, handle, depth, mem
 
@@ -87,6 +91,7 @@ class CompletionQueue:
         return self.ctx._lib.rn_cq_dev(self._c)
 
     def poll(self, max_entries: int = 16) -> List[WorkCompletion]:
+        """Consume up to ``max_entries`` completions that are ready now (never blocks)."""
         arr = (N.RnWc * max_entries)()
         n = self.ctx._lib.rn_poll_cq(self._c, max_entries, arr)
         if n < 0:
@@ -95,6 +100,7 @@ class CompletionQueue:
                                bool(a.is_error)) for a in arr[:n]]
 
     def wait(self, n: int = 1, timeout_s: float = 5.0) -> List[WorkCompletion]:
+        """Poll until ``n`` completions have been consumed; ``TimeoutError`` after ``timeout_s``."""
         import time
         out: List[WorkCompletion] = []
         t0 = time.monotonic()
@@ -106,6 +112,7 @@ class CompletionQueue:
 
 
 class QueuePair:
+    """A reliable-connected queue pair: send queue of 64-byte WQEBBs, receive queue, doorbell record and doorbell register, in device memory (GPU posters) or pinned host memory (host posters).  RESET -> INIT -> RTR -> RTS as in IB."""
     def __init__(self, ctx, handle, scq, rcq, sq_depth, rq_depth, sq_mem):
         self.ctx, self._q, self.scq, self.rcq = ctx, handle, scq, rcq
         self.sq_depth, self.rq_depth, self.sq_mem = sq_depth, rq_depth, sq_mem
@@ -117,17 +124,21 @@ class QueuePair:
 
     @property
     def state(self) -> str:
+        """Current IB state name (RESET, INIT, RTR, RTS, SQD, SQE, ERR)."""
         return W.QP_STATE_NAMES[self.ctx._lib.rn_qp_state(self._q)]
 
     def modify(self, state: int):
+        """``ibv_modify_qp``: checked state transition (``wire.QPS_*``); RESET rewinds every index and the doorbell."""
         N.check(self.ctx._lib.rn_modify_qp(self._q, state), "modify_qp")
 
     def describe(self) -> N.RnRemote:
+        """What a requester must know to target this QP as a responder (receive ring, receive CQ, MKey table, QP number)."""
         r = N.RnRemote()
         N.check(self.ctx._lib.rn_qp_describe(self._q, C.byref(r)), "qp_describe")
         return r
 
     def connect_remote(self, remote: N.RnRemote):
+        """Install an already translated description of the responder (see ``parallel.peer.connect_to``)."""
         N.check(self.ctx._lib.rn_qp_connect(self._q, C.byref(remote)), "qp_connect")
 
     def connect(self, peer: Optional["QueuePair"] = None):
@@ -146,25 +157,30 @@ class QueuePair:
 
     def post_write(self, src: MemoryRegion, dst: MemoryRegion, nbytes=None, src_off=0, dst_off=0, signaled=True,
                    imm=None) -> int:
+        """Host-posted RDMA WRITE (``imm`` not None: WRITE_WITH_IMM, consumes a receive WQE at the responder).  Returns the WQE index."""
         n = src.length - src_off if nbytes is None else nbytes
         op = W.OP_RDMA_WRITE if imm is None else W.OP_RDMA_WRITE_IMM
         return self._post(op, src.addr + src_off, src.lkey, dst.addr + dst_off, dst.rkey, n, signaled, imm or 0)
 
     def post_read(self, dst_local: MemoryRegion, src_remote: MemoryRegion, nbytes=None, local_off=0, remote_off=0,
                   signaled=True) -> int:
+        """Host-posted RDMA READ into ``dst_local``.  Returns the WQE index."""
         n = dst_local.length - local_off if nbytes is None else nbytes
         return self._post(W.OP_RDMA_READ, dst_local.addr + local_off, dst_local.lkey, src_remote.addr + remote_off,
                           src_remote.rkey, n, signaled)
 
     def post_send(self, src: MemoryRegion, nbytes=None, src_off=0, signaled=True, imm=None) -> int:
+        """Host-posted SEND (``imm`` not None: SEND_WITH_IMM); lands in the responder's next receive buffer."""
         n = src.length - src_off if nbytes is None else nbytes
         op = W.OP_SEND if imm is None else W.OP_SEND_IMM
         return self._post(op, src.addr + src_off, src.lkey, 0, 0, n, signaled, imm or 0)
 
     def post_raw(self, opcode, laddr=0, lkey=0, raddr=0, rkey=0, nbytes=0, signaled=True, imm=0) -> int:
+        """Post a WQE with arbitrary fields (error-path tests: bad keys, bad opcodes, NOP)."""
         return self._post(opcode, laddr, lkey, raddr, rkey, nbytes, signaled, imm)
 
     def post_recv(self, dst: MemoryRegion, nbytes=None, off=0):
+        """Post one receive buffer (consumed in order by SEND / WRITE_WITH_IMM)."""
         n = dst.length - off if nbytes is None else nbytes
         N.check(self.ctx._lib.rn_post_recv(self._q, dst.addr + off, dst.lkey, n), "post_recv")
 
@@ -175,6 +191,7 @@ class QueuePair:
                                               -1 if trace is None else int(trace)), "qp_set_flags")
 
     def read_trace(self, nslots: Optional[int] = None) -> List[dict]:
+        """Per-SQ-slot %globaltimer stamps (post, claim, parsed, copied, cqe, seen); needs ``set_flags(trace=True)``."""
         n = nslots or self.sq_depth
         buf = (C.c_uint64 * (n * 8))()
         N.check(self.ctx._lib.rn_qp_read_trace(self._q, buf, n), "qp_read_trace")
@@ -182,6 +199,7 @@ class QueuePair:
         return [{k: buf[i * 8 + j] for j, k in enumerate(names)} for i in range(n)]
 
     def counters(self) -> dict:
+        """Engine-side counters of this QP (WQEs, CQEs, errors, bytes, RNR waits, doorbell-order violations) and its queue indices."""
         c = N.RnQpCounters()
         N.check(self.ctx._lib.rn_qp_query(self._q, C.byref(c)), "qp_query")
         d = {k: getattr(c, k) for k, _ in c._fields_ if k != "pad"}
@@ -275,6 +293,7 @@ class Context:
 
     # ---- registration
     def classify(self, buf) -> str:
+        """Where a buffer lives as the HCA sees it: device / pinned host / pageable host / managed."""
         ptr, _ = _ptr_len(buf, 1)
         dev = C.c_int(-1)
         return ["host", "device", "pinned_host", "managed"][self._lib.rn_classify_ptr(ptr, C.byref(dev))]
@@ -301,12 +320,14 @@ class Context:
 
     # ---- queues
     def create_cq(self, depth: int = 1024, mem: int = W.MEM_DEVICE) -> CompletionQueue:
+        """``ibv_create_cq``; ``mem`` = ``wire.MEM_DEVICE`` (GPU pollers) or ``wire.MEM_HOST_PINNED`` (CPU pollers)."""
         c = C.c_void_p()
         N.check(self._lib.rn_create_cq(self._h, depth, mem, C.byref(c)), "create_cq")
         return CompletionQueue(self, c, depth, mem)
 
     def create_qp(self, scq: CompletionQueue, rcq: Optional[CompletionQueue] = None, sq_depth: int = 256,
                   rq_depth: int = 256, sq_mem: int = W.MEM_DEVICE, chunk_bytes: int = 512 << 10) -> QueuePair:
+        """``ibv_create_qp`` (RC).  ``sq_mem`` places the rings and doorbells in device memory (posted by kernels) or pinned host memory (posted by the CPU); ``chunk_bytes`` is the engine's minimum work granule for this QP."""
         q = C.c_void_p()
         rcq = rcq or scq
         N.check(self._lib.rn_create_qp(self._h, scq._c, rcq._c, sq_depth, rq_depth, sq_mem, chunk_bytes, C.byref(q)),
@@ -315,11 +336,13 @@ class Context:
 
     def loopback_qp(self, depth: int = 256, mem: int = W.MEM_DEVICE, chunk_bytes: int = 512 << 10,
                     cq_depth: Optional[int] = None) -> QueuePair:
+        """A QP connected to itself with one CQ for sends and receives: the single-GPU wire of configs 2, 3 and 5."""
         cq = self.create_cq(cq_depth or max(2 * depth, 64), mem)
         return self.create_qp(cq, cq, depth, depth, mem, chunk_bytes).connect()
 
     # ---- engine
     def engine_start(self, ctas: int = 32, idle_timeout_ms: int = 5000, rnr_timeout_ms: int = 500):
+        """Launch the persistent DMA engine on ``ctas`` SMs.  Allocate and register everything first: cudaMalloc, stream creation and first-time kernel loads all wait for a resident kernel.  It leaves by itself after ``idle_timeout_ms`` without work."""
         N.check(self._lib.rn_engine_start(self._h, ctas, idle_timeout_ms, rnr_timeout_ms), "engine_start")
 
     def engine_run_oneshot(self, ctas: int = 32):
@@ -335,6 +358,7 @@ class Context:
             self._lib.rn_engine_set_oneshot(self._h, 0)
 
     def engine_stop(self):
+        """Ask the engine to leave and wait for it; reports an engine fault as a RuntimeWarning."""
         N.check(self._lib.rn_engine_stop(self._h), "engine_stop")
         self._report_engine_fault()
 
@@ -354,17 +378,21 @@ class Context:
 
     @property
     def engine_running(self) -> bool:
+        """True while the engine kernel is resident."""
         return bool(self._lib.rn_engine_running(self._h))
 
     def engine_stats(self) -> dict:
+        """Engine-wide counters: bulk chunks moved, start / exit %globaltimer, CTAs, idle-exit and fatal flags."""
         s = N.RnEngineStats()
         N.check(self._lib.rn_engine_stats(self._h, C.byref(s)), "engine_stats")
         return {k: getattr(s, k) for k, _ in s._fields_}
 
     def mkey_table_ptr(self) -> int:
+        """Device address of this HCA's MKey table (what a peer's engine translates rkeys with)."""
         return self._lib.rn_hca_mkey_table(self._h)
 
     def close(self):
+        """Stop the engine and free the HCA (queues, CQs, control arenas).  Registered tensors are untouched."""
         if not self._closed:
             self._closed = True
             self._lib.rn_hca_close(self._h)
