@@ -4,7 +4,6 @@ from __future__ import annotations
 
 import ctypes as C
 from dataclasses import dataclass
-from typing import Optional
 
 import torch
 

@@ -3,12 +3,11 @@ from __future__ import annotations
 
 import ctypes as C
 from dataclasses import dataclass
-from typing import List, Sequence
+from typing import List
 
 import torch
 
 from .. import _native as N
-from .. import wire as W
 
 WAIT_STATUS = {0: "OK", -1: "TIMEOUT", -2: "CQE_ERROR", -3: "QP_ERROR"}
 

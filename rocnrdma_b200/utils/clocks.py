@@ -4,7 +4,6 @@ from __future__ import annotations
 import statistics
 import subprocess
 import threading
-import time
 from typing import List, Optional
 
 _QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"

@@ -61,8 +61,6 @@ def test_pack_only_matches_reference_bit_exact(ctx, n_chunks, chunk):
 @pytest.mark.gpu
 @pytest.mark.parametrize("with_imm", [False, True])
 def test_fused_pack_and_rdma_write(ctx, with_imm):
-    import rocnrdma_b200 as rn
-    from rocnrdma_b200 import wire as W
     chunk, n_chunks = 1 << 18, 16
     x = _payload(chunk * n_chunks, "cuda:0", seed=9)
     nb = P.staging_bytes(x.numel(), chunk)

@@ -1,5 +1,5 @@
 """Regenerate profiles/sass/*.sass and summary.json from the built library (CPU only: cuobjdump)."""
-import collections, json, os, re, subprocess, sys
+import collections, json, os, re, subprocess
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = os.path.join(root, "rocnrdma_b200", "lib", "librocnrdma_b200.so")
 out = os.path.join(root, "profiles", "sass")
