@@ -107,7 +107,9 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             sys.stderr.write(f"--- {src}\n{out}\n")
     if failed:
         raise RuntimeError("native build failed")
-    (LIBDIR / "ptxas_info.txt").write_text("\n".join(f"=== {k}\n{v}" for k, v in logs.items()))
+    # register / shared-memory / spill summary per kernel (tracked: it is evidence); compile times are noise
+    keep = lambda v: "\n".join(l for l in v.splitlines() if "Compile time" not in l)
+    (LIBDIR / "ptxas_info.txt").write_text("\n".join(f"=== {k}\n{keep(v)}" for k, v in logs.items()))
     link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *map(str, objs),
             "-Xcompiler", "-fPIC", "-ldl", "-lpthread"]
     subprocess.run(link, check=True)
