@@ -4,8 +4,6 @@ import runpy
 
 import pytest
 
-pytestmark = pytest.mark.gpu
-
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -16,6 +14,7 @@ def test_readme_snippet_and_example_are_the_same_text():
     assert code in open(os.path.join(ROOT, "examples", "quickstart.py")).read()
 
 
+@pytest.mark.gpu
 def test_quickstart_runs(capsys):
     runpy.run_path(os.path.join(ROOT, "examples", "quickstart.py"), run_name="__main__")
     out = capsys.readouterr().out
