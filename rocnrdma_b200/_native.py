@@ -37,6 +37,29 @@ class RnQpCounters(C.Structure):
                 ("sq_cons", u64), ("cursor", u64), ("retire_head", u64), ("state", u32), ("pad", u32)]
 
 
+class RnVWc(C.Structure):
+    _fields_ = [("wr_id", u64), ("status", u32), ("opcode", u32), ("byte_len", u32), ("imm", u32), ("qp_num", u32),
+                ("vendor_err", u32), ("with_imm", u32), ("pad", u32)]
+
+
+class RnRawQp(C.Structure):
+    _fields_ = [("sq_buf", u64), ("sq_wqe_cnt", u32), ("sq_stride", u32), ("rq_buf", u64), ("rq_wqe_cnt", u32), ("rq_stride", u32),
+                ("dbrec", u64), ("bf_reg", u64), ("bf_size", u32), ("qpn", u32),
+                ("cq_buf", u64), ("cq_cqe_cnt", u32), ("cq_cqe_size", u32), ("cq_dbrec", u64), ("cqn", u32), ("pad0", u32),
+                ("rcq_buf", u64), ("rcq_cqe_cnt", u32), ("rcq_cqe_size", u32), ("rcq_dbrec", u64), ("rcqn", u32), ("pad1", u32)]
+
+
+class RnGpuQp(C.Structure):
+    _fields_ = [("sq_dev", u64), ("rq_dev", u64), ("dbrec_dev", u64), ("bf_dev", u64), ("cq_dev", u64), ("cq_dbrec_dev", u64),
+                ("rcq_dev", u64), ("rcq_dbrec_dev", u64), ("sq_wqe_cnt", u32), ("rq_wqe_cnt", u32), ("cq_cqe_cnt", u32),
+                ("rcq_cqe_cnt", u32), ("qpn", u32), ("cqn", u32), ("rcqn", u32), ("flags", u32)]
+
+
+class RnMockQpStats(C.Structure):
+    _fields_ = [("n_wqe", u64), ("n_cqe", u64), ("n_err", u64), ("n_bytes", u64), ("n_rnr", u64), ("n_db_no_progress", u64),
+                ("n_doorbells", u64), ("hw_sq_cons", u64), ("sq_cq_overruns", u64)]
+
+
 class RnEngineStats(C.Structure):
     _fields_ = [("n_bulk_chunks", u64), ("t_start", u64), ("t_exit", u64), ("running_ctas", u32),
                 ("exited_idle", u32), ("fatal", u32), ("n_qps", u32), ("ctas", u32), ("pad", u32)]
@@ -124,6 +147,45 @@ _SIGS = {
     "rn_k_checksum": (i32, [u64, u64, u64, u64]),
     "rn_k_compare": (i32, [u64, u64, u64, u64, u64]),
     "rn_k_l2_flush": (i32, [u64, u64, u64, u32]),
+    # ---- ConnectX backend (csrc/verbs/verbs_dl.cc): libibverbs / mlx5dv through dlopen
+    "rn_qp_adopt": (i32, [vp, C.POINTER(RnGpuQp), C.POINTER(vp)]),
+    "rn_qp_is_adopted": (i32, [vp]),
+    "rn_verbs_compiled": (i32, []),
+    "rn_verbs_why": (C.c_char_p, []),
+    "rn_verbs_is_mock": (i32, []),
+    "rn_verbs_libdir": (C.c_char_p, []),
+    "rn_verbs_available": (i32, []),
+    "rn_verbs_device_name": (i32, [i32, C.c_char_p, i32]),
+    "rn_verbs_open": (vp, [C.c_char_p, i32, i32, i32]),
+    "rn_verbs_close": (i32, [vp]),
+    "rn_verbs_dev_name": (C.c_char_p, [vp]),
+    "rn_verbs_port_active": (i32, [vp]),
+    "rn_verbs_link_layer": (i32, [vp]),
+    "rn_verbs_local_addr": (i32, [vp, C.POINTER(u16), C.POINTER(u8)]),
+    "rn_verbs_reg_mr": (vp, [vp, u64, u64, i32, i32, u64, u32, C.POINTER(u32), C.POINTER(u32)]),
+    "rn_verbs_dereg_mr": (i32, [vp]),
+    "rn_verbs_create_cq": (vp, [vp, i32]),
+    "rn_verbs_destroy_cq": (i32, [vp]),
+    "rn_verbs_create_qp": (vp, [vp, vp, vp, u32, u32]),
+    "rn_verbs_destroy_qp": (i32, [vp]),
+    "rn_verbs_qpn": (u32, [vp]),
+    "rn_verbs_qp_state": (u32, [vp]),
+    "rn_verbs_connect": (i32, [vp, u32, u16, C.POINTER(u8)]),
+    "rn_verbs_set_state": (i32, [vp, u32]),
+    "rn_verbs_post_send": (i32, [vp, u32, u64, u32, u64, u32, u32, i32, u32, C.POINTER(u64)]),
+    "rn_verbs_post_recv": (i32, [vp, u64, u32, u32, C.POINTER(u64)]),
+    "rn_verbs_poll": (i32, [vp, i32, C.POINTER(RnVWc)]),
+    "rn_verbs_host_stream": (i32, [vp, u32, u64, u32, u64, u32, u32, u32, u32, u64, u32, u64, C.POINTER(u64), C.POINTER(u32)]),
+    "rn_verbs_host_staged_stream": (i32, [vp, u64, u64, u64, u32, u64, u32, u32, u32, u64, u32, u64, C.POINTER(u64)]),
+    "rn_verbs_raw_qp": (i32, [vp, C.POINTER(RnRawQp)]),
+    "rn_verbs_db_proxy_attach": (i32, [vp, C.POINTER(u64)]),
+    "rn_verbs_db_proxy_forwarded": (u64, [vp]),
+    "rn_verbs_map_qp_to_gpu": (i32, [vp, C.POINTER(RnGpuQp)]),
+    "rn_verbs_mock_qp_stats": (i32, [vp, C.POINTER(RnMockQpStats)]),
+    "rn_verbs_mock_declare_gpu_range": (i32, [u64, u64]),
+    "rn_verbs_mock_gpu_free": (i32, [u64]),
+    "rn_verbs_mock_set_rnr_timeout_ms": (i32, [u64]),
+    "rn_verbs_mock_bridge_status": (C.c_char_p, []),
 }
 
 # Symbols that later build stages add; bound when present so partial builds import.
@@ -149,6 +211,17 @@ def _bind(lib, name, restype, argtypes, optional=False):
 
 def lib_path() -> Path:
     return _LIB_PATH
+
+
+def mock_verbs_dir() -> Path:
+    """Directory of the in-tree mock rdma-core provider (libibverbs.so.1 / libmlx5.so.1 look-alikes)."""
+    return _LIB_PATH.parent / "mock"
+
+
+def use_mock_verbs():
+    """Point the ConnectX backend at the mock provider.  Must run before the backend is first used in this
+    process (the libraries are dlopen()ed once); an explicit ROCNRDMA_VERBS_LIBDIR wins."""
+    os.environ.setdefault("ROCNRDMA_VERBS_LIBDIR", str(mock_verbs_dir()))
 
 
 def available() -> bool:

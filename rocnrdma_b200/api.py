@@ -9,6 +9,15 @@
     qp.post_write(src_mr, dst_mr, nbytes)        # host-posted   (baseline: SURVEY.md B2)
     ops.rdma_stream(qp, ...)                     # GPU-posted    (product:  SURVEY.md P1)
 
+Two wires sit under the same objects (``Context(wire=...)``):
+
+* ``softhca`` -- the software HCA: queues in GPU or pinned memory, a persistent sm_100a kernel moves
+  the bytes.  What runs when the box exposes no NIC.
+* ``verbs``   -- a ConnectX through libibverbs / mlx5dv (``csrc/verbs/verbs_dl.cc``): ``reg_mr`` is
+  ``ibv_reg_dmabuf_mr`` / ``ibv_reg_mr`` on the GPU pointer, host-posted verbs are ``ibv_post_send``,
+  and ``loopback_qp(mem=MEM_DEVICE)`` hands the raw mlx5 queues to the GPU so the same kernels post
+  to the NIC.  ``auto`` picks it when a real HCA is reachable.
+
 Reference parity: ``reg_mr`` is what amdp2p's seven peer-memory callbacks make
 possible (amdp2p.c:363-371); revocation (``MemoryRegion.revoke``) is
 free_callback (amdp2p.c:88-109).  Everything below registration has no
@@ -20,8 +29,29 @@ import ctypes as C
 from dataclasses import dataclass
 from typing import List, Optional
 
+import os
+
 from . import _native as N
 from . import wire as W
+
+# ibv_wc_status -> the syndrome names the softhca wire reports (wire.SYNDROMES), so callers see one vocabulary
+_WC_STATUS = {0: "OK", 1: "LOCAL_LENGTH_ERR", 2: "LOCAL_QP_OP_ERR", 4: "LOCAL_PROT_ERR", 5: "WR_FLUSH_ERR", 6: "MW_BIND_ERR",
+              7: "BAD_RESP_ERR", 8: "LOCAL_ACCESS_ERR", 9: "REMOTE_INVAL_REQ_ERR", 10: "REMOTE_ACCESS_ERR", 11: "REMOTE_OP_ERR",
+              12: "TRANSPORT_RETRY_EXC_ERR", 13: "RNR_RETRY_EXC_ERR", 16: "REMOTE_ABORTED_ERR", 21: "GENERAL_ERR"}
+_IBV_WC_RECV, _IBV_WC_RECV_RDMA_WITH_IMM = 128, 129
+
+
+def resolve_wire(wire: str = "auto") -> str:
+    """'auto' -> 'verbs' when a REAL HCA is usable (libibverbs loads, /dev/infiniband is there, a device
+    exists), else 'softhca'.  The mock provider is never picked automatically: ask for it with
+    ``wire="verbs"`` (or ROCNRDMA_WIRE=verbs) after ``_native.use_mock_verbs()``."""
+    wire = os.environ.get("ROCNRDMA_WIRE", wire) if wire == "auto" else wire
+    if wire not in ("auto", "softhca", "verbs"):
+        raise ValueError(f"wire={wire!r}: expected auto | softhca | verbs")
+    if wire != "auto":
+        return wire
+    lib = N.load()
+    return "verbs" if lib.rn_verbs_available() > 0 and not lib.rn_verbs_is_mock() else "softhca"
 
 
 def _ptr_len(buf, nbytes=None):
@@ -46,36 +76,58 @@ class WorkCompletion:
     syndrome: int
     wqe_opcode: int
     is_error: bool
+    status_name: Optional[str] = None      # verbs wire: the ibv_wc_status, in the same vocabulary
+    wr_id: int = 0
 
     @property
     def status(self) -> str:
-        return W.SYNDROMES.get(self.syndrome, hex(self.syndrome))
+        return self.status_name or W.SYNDROMES.get(self.syndrome, hex(self.syndrome))
 
 
 class MemoryRegion:
     """A registered range (what ``ibv_reg_mr`` returns): ``addr``/``length``, one key used as lkey and rkey (mlx5 style), access bits; ``state`` follows PINNED -> REVOKED -> FREE."""
-    def __init__(self, ctx: "Context", addr: int, length: int, key: int, access: int, keepalive=None):
+    def __init__(self, ctx: "Context", addr: int, length: int, key: int, access: int, keepalive=None, rkey: Optional[int] = None,
+                 vmr=None):
         self.ctx, self.addr, self.length, self.key, self.access = ctx, addr, length, key, access
-        self.lkey = self.rkey = key
+        self.lkey = key
+        self.rkey = key if rkey is None else rkey
         self._keepalive = keepalive
         self._live = True
+        self._vmr = vmr               # verbs wire: the ibv_mr handle
+        self.dmabuf_fd = -1
+        self.mode = "direct"
 
     @property
     def state(self) -> str:
         """FREE / PINNED / REVOKED, read from the HCA."""
+        if self._vmr is not None or self.ctx.wire == "verbs":
+            return "PINNED" if self._live else "FREE"
         return ["FREE", "PINNED", "REVOKED"][self.ctx._lib.rn_mr_state(self.ctx._h, self.key)]
 
     def revoke(self):
         """The backing memory is going away: stop translating now (the engine fails
         any WQE that names this key with a protection error)."""
+        if self.ctx.wire == "verbs":
+            raise N.NativeError("revocation on the verbs wire is the GPU driver's call (free the memory): "
+                                "the peer-memory client's free callback invalidates the MR (kmod/b200p2p.c)")
         N.check(self.ctx._lib.rn_mr_revoke(self.ctx._h, self.key), "mr_revoke")
 
     def dereg(self):
         """Release the MKey slot (and the dma-buf pin, if any).  Safe after ``revoke``."""
-        if self._live:
+        if not self._live:
+            return
+        if self._vmr is not None:
+            rc = self.ctx._lib.rn_verbs_dereg_mr(self._vmr)
+            self._vmr = None
+            if self.dmabuf_fd >= 0:
+                self.ctx._lib.rn_dmabuf_close(self.dmabuf_fd)
+                self.dmabuf_fd = -1
+            if rc:
+                raise N.NativeError(f"ibv_dereg_mr failed ({rc})")
+        else:
             N.check(self.ctx._lib.rn_dereg_mr(self.ctx._h, self.key), "dereg_mr")
-            self._live = False
-            self._keepalive = None
+        self._live = False
+        self._keepalive = None
 
     def __repr__(self):
         return f"MemoryRegion(addr=0x{self.addr:x}, len={self.length}, key=0x{self.key:x})"
@@ -83,15 +135,37 @@ class MemoryRegion:
 
 class CompletionQueue:
     """A completion queue: 64-byte mlx5 CQEs with an owner bit, in device or pinned host memory.  Device posters poll it themselves; these methods are the host-side consumer."""
-    def __init__(self, ctx, handle, depth, mem):
+    def __init__(self, ctx, handle, depth, mem, vcq=None):
         self.ctx, self._c, self.depth, self.mem = ctx, handle, depth, mem
+        self._vcq = vcq               # verbs wire: the ibv_cq handle
 
     @property
     def dev_ptr(self) -> int:
+        if self._c is None:
+            raise N.NativeError("this CQ belongs to the HCA; it has a device view only once its QP was handed to the GPU")
         return self.ctx._lib.rn_cq_dev(self._c)
 
     def poll(self, max_entries: int = 16) -> List[WorkCompletion]:
         """Consume up to ``max_entries`` completions that are ready now (never blocks)."""
+        if self._vcq is not None:
+            n_max = min(max_entries, 32)
+            varr = (N.RnVWc * n_max)()
+            n = self.ctx._lib.rn_verbs_poll(self._vcq, n_max, varr)
+            if n < 0:
+                raise N.NativeError(f"ibv_poll_cq failed ({n})")
+            out = []
+            for a in varr[:n]:
+                recv = a.opcode >= _IBV_WC_RECV
+                err = a.status != 0
+                if recv:
+                    opc = W.CQE_RESP_ERR if err else (W.CQE_RESP_WR_IMM if a.opcode == _IBV_WC_RECV_RDMA_WITH_IMM else
+                                                      (W.CQE_RESP_SEND_IMM if a.with_imm else W.CQE_RESP_SEND))
+                else:
+                    opc = W.CQE_REQ_ERR if err else W.CQE_REQ
+                name = _WC_STATUS.get(a.status, f"IBV_WC_{a.status}")
+                out.append(WorkCompletion(a.qp_num, a.wr_id & 0xFFFF, opc, a.byte_len, a.imm, W.SYN.get(name, 0xFF if err else 0), 0,
+                                          err, status_name=name, wr_id=a.wr_id))
+            return out
         arr = (N.RnWc * max_entries)()
         n = self.ctx._lib.rn_poll_cq(self._c, max_entries, arr)
         if n < 0:
@@ -207,22 +281,187 @@ class QueuePair:
         return d
 
 
+class VerbsQueuePair(QueuePair):
+    """An RC QP of a real HCA (verbs wire).  Host-posted by default (``ibv_post_send``: baselines B0 / B2);
+    ``to_gpu()`` maps its mlx5 queues and doorbell register into the GPU and wraps them in the device-side
+    ``QpDev`` the kernels post to (IBGDA) -- after that the host must not post to it any more."""
+    def __init__(self, ctx, vq, scq, rcq, sq_depth, rq_depth, sq_mem):
+        self.ctx, self._vq, self.scq, self.rcq = ctx, vq, scq, rcq
+        self.sq_depth, self.rq_depth, self.sq_mem = sq_depth, rq_depth, sq_mem
+        self._q = None                       # the adopted (GPU-visible) view, once to_gpu() ran
+        self.qpn = ctx._lib.rn_verbs_qpn(vq)
+        self.db_proxy = False
+        self._peer = None
+
+    @property
+    def on_gpu(self) -> bool:
+        return self._q is not None
+
+    @property
+    def dev_ptr(self) -> int:
+        if self._q is None:
+            raise N.NativeError("this QP is host-posted; call to_gpu() (or create it with mem=MEM_DEVICE) before launching kernels on it")
+        return self.ctx._lib.rn_qp_dev(self._q)
+
+    @property
+    def state(self) -> str:
+        return W.QP_STATE_NAMES[min(self.ctx._lib.rn_verbs_qp_state(self._vq), 6)]
+
+    def modify(self, state: int):
+        """Only the attribute-less transitions (RESET, ERR); ``connect`` walks INIT -> RTR -> RTS."""
+        if state not in (W.QPS_RESET, W.QPS_ERR):
+            raise N.NativeError("verbs wire: use connect() for INIT/RTR/RTS")
+        self._vcheck(self.ctx._lib.rn_verbs_set_state(self._vq, state), "modify_qp")
+
+    def _vcheck(self, rc, what):
+        if rc:
+            raise N.NativeError(f"{what} failed (rc={rc}): {self.ctx._lib.rn_verbs_why().decode(errors='replace')}")
+
+    def address(self):
+        """(qpn, lid, gid bytes): what the other side needs for its RTR transition (exchanged out of band)."""
+        lid = C.c_uint16()
+        gid = (C.c_uint8 * 16)()
+        self.ctx._lib.rn_verbs_local_addr(self.ctx._vdev, C.byref(lid), gid)
+        return self.qpn, lid.value, bytes(gid)
+
+    def connect_to(self, qpn: int, lid: int, gid: bytes = b""):
+        g = (C.c_uint8 * 16)(*gid) if gid and not lid else None
+        self._vcheck(self.ctx._lib.rn_verbs_connect(self._vq, qpn, lid, g), "connect")
+        return self
+
+    def connect(self, peer: Optional["QueuePair"] = None):
+        """Bring this QP and ``peer`` (default: itself -- loopback through the port) to RTS.  ``peer`` may live on
+        another HCA (NIC0 -> NIC1) as long as both are reachable from this process."""
+        peer = peer or self
+        self.connect_to(*peer.address())
+        if peer is not self:
+            peer.connect_to(*self.address())
+        self._peer, peer._peer = peer, self
+        if self.sq_mem == W.MEM_DEVICE:
+            self.to_gpu()
+        if peer is not self and peer.sq_mem == W.MEM_DEVICE:
+            peer.to_gpu()
+        return self
+
+    def describe(self):
+        raise N.NativeError("verbs wire: peers exchange address() tuples, not softhca descriptors")
+
+    connect_remote = describe
+
+    def to_gpu(self):
+        """mlx5dv_init_obj + cudaHostRegister: SQ / RQ / doorbell record / CQs (host memory the NIC reads) and the
+        BlueFlame register (MMIO) become GPU-addressable; ``dev_ptr`` is then what ``ops.rdma_stream``,
+        ``ops.pack_fp8_write`` and ``ops.gemm_send`` take.  Falls back to a CPU doorbell proxy when the UAR page
+        cannot be mapped (``db_proxy`` says which)."""
+        if self._q is not None:
+            return self
+        if self.ctx._h is None:
+            raise N.NativeError("to_gpu() needs a context bound to a GPU (device=None is host-only)")
+        g = N.RnGpuQp()
+        N.load().rn_set_device(self.ctx.device)
+        self._vcheck(self.ctx._lib.rn_verbs_map_qp_to_gpu(self._vq, C.byref(g)), "map_qp_to_gpu")
+        q = C.c_void_p()
+        N.check(self.ctx._lib.rn_qp_adopt(self.ctx._h, C.byref(g), C.byref(q)), "qp_adopt")
+        self._q = q
+        self.db_proxy = bool(g.flags & 1)
+        self.raw = {k: getattr(g, k) for k, _ in g._fields_}
+        return self
+
+    def raw_queues(self) -> dict:
+        """The mlx5dv view (host addresses and geometry of SQ / RQ / doorbell record / BlueFlame register / CQs)."""
+        r = N.RnRawQp()
+        self._vcheck(self.ctx._lib.rn_verbs_raw_qp(self._vq, C.byref(r)), "raw_qp")
+        return {k: getattr(r, k) for k, _ in r._fields_ if not k.startswith("pad")}
+
+    def _post(self, opcode, laddr, lkey, raddr, rkey, nbytes, signaled=True, imm=0) -> int:
+        wr = C.c_uint64()
+        self._vcheck(self.ctx._lib.rn_verbs_post_send(self._vq, opcode, laddr, lkey, raddr, rkey, nbytes, int(bool(signaled)), imm,
+                                                      C.byref(wr)), "post_send")
+        return wr.value
+
+    def post_recv(self, dst: MemoryRegion, nbytes=None, off=0):
+        n = dst.length - off if nbytes is None else nbytes
+        self._vcheck(self.ctx._lib.rn_verbs_post_recv(self._vq, dst.addr + off, dst.lkey, n, None), "post_recv")
+
+    def set_flags(self, sys_scope: Optional[bool] = None, trace: Optional[bool] = None):
+        if self._q is not None:
+            super().set_flags(sys_scope, trace)
+
+    def read_trace(self, nslots: Optional[int] = None) -> List[dict]:
+        if self._q is None:
+            return []
+        return super().read_trace(nslots)
+
+    def counters(self) -> dict:
+        """Poster-side indices (when on the GPU) plus, on the mock provider, the NIC's own counters
+        (``n_db_order_violations`` = doorbells that arrived before the doorbell record moved)."""
+        d = {"n_wqe": 0, "n_cqe": 0, "n_err": 0, "n_db_order_violations": 0, "n_bytes": 0, "n_rnr": 0}
+        if self._q is not None:
+            c = N.RnQpCounters()
+            N.check(self.ctx._lib.rn_qp_query(self._q, C.byref(c)), "qp_query")
+            d.update({k: getattr(c, k) for k in ("resv_head", "ready_head", "sq_cons")})
+        st = N.RnMockQpStats()
+        if self.ctx._lib.rn_verbs_mock_qp_stats(self._vq, C.byref(st)) == 0:
+            d.update(n_wqe=st.n_wqe, n_cqe=st.n_cqe, n_err=st.n_err, n_bytes=st.n_bytes, n_rnr=st.n_rnr,
+                     n_db_order_violations=st.n_db_no_progress, n_doorbells=st.n_doorbells, cq_overruns=st.sq_cq_overruns)
+            d["nic"] = "mock"
+        d["state"] = self.state
+        d["db_proxy_forwarded"] = self.ctx._lib.rn_verbs_db_proxy_forwarded(self._vq)
+        return d
+
+    def destroy(self):
+        if self._vq is not None:
+            self.ctx._lib.rn_verbs_destroy_qp(self._vq)
+            self._vq = None
+
+
 class Context:
     """One software HCA bound to one GPU (one per process in multi-GPU runs)."""
 
     def __init__(self, device: int = 0, max_mkeys: int = 1024, max_qps: int = 256, arena_bytes: int = 64 << 20,
-                 host_arena_bytes: int = 16 << 20):
+                 host_arena_bytes: int = 16 << 20, wire: str = "auto", nic=None, port: int = 1, gid_index: int = 0):
+        """``wire``: ``softhca`` | ``verbs`` | ``auto`` (see :func:`resolve_wire`).  On the verbs wire ``nic`` names
+        the HCA (``"mlx5_3"``) or gives its index (default: the GPU's index, the usual GPU i <-> NIC i pairing)."""
         self._lib = N.load()
+        self.wire = resolve_wire(wire)
+        self._vdev = None
+        self._vqps: List["VerbsQueuePair"] = []
+        self._vcqs: List[CompletionQueue] = []
         h = C.c_void_p()
-        N.check(self._lib.rn_hca_open(device, max_mkeys, max_qps, arena_bytes, host_arena_bytes, C.byref(h)), "hca_open")
+        # The HCA object also backs the verbs wire: pre-created streams, the mapped result scratch, and the
+        # device arena that holds the QpDev / CqDev views of adopted mlx5 queues.  ``device=None`` (verbs wire
+        # only) is a host-only context: registration of host memory and host-posted verbs, no GPU needed
+        # (BASELINE config 1: host-DRAM loopback between two ports).
+        if device is None:
+            if self.wire != "verbs":
+                raise ValueError("a host-only context (device=None) needs wire='verbs'")
+            h = None
+        else:
+            N.check(self._lib.rn_hca_open(device, max_mkeys, max_qps, arena_bytes, host_arena_bytes, C.byref(h)), "hca_open")
         self._h = h
         self.device = device
+        if self.wire == "verbs":
+            if self._lib.rn_verbs_available() <= 0:
+                why = self._lib.rn_verbs_why().decode(errors="replace")
+                if self._h:
+                    self._lib.rn_hca_close(self._h)
+                raise N.NativeError(f"wire='verbs' but no RDMA device is usable: {why}")
+            name = nic.encode() if isinstance(nic, str) else b""
+            index = nic if isinstance(nic, int) else (device or 0)
+            self._vdev = self._lib.rn_verbs_open(name, index, port, gid_index)
+            if not self._vdev:
+                why = self._lib.rn_verbs_why().decode(errors="replace")
+                if self._h:
+                    self._lib.rn_hca_close(self._h)
+                raise N.NativeError(f"cannot open the HCA: {why}")
+            self.nic = self._lib.rn_verbs_dev_name(self._vdev).decode()
+            self.nic_is_mock = bool(self._lib.rn_verbs_is_mock())
         self._mrs: List[MemoryRegion] = []
         self._closed = False
         self.last_engine_fatal = 0
         self._stream = None
         sz = C.c_uint64()
-        self._scratch_ptr = self._lib.rn_hca_scratch(self._h, C.byref(sz))
+        self._scratch_ptr = self._lib.rn_hca_scratch(self._h, C.byref(sz)) if self._h else 0
         self._scratch_size = sz.value
 
     @property
@@ -303,15 +542,50 @@ class Context:
         fd through the CUDA driver (``MemoryRegion.dmabuf_fd``) -- the handle an HCA takes in
         ``ibv_reg_dmabuf_mr`` -- which pins the GPU pages for as long as the region lives."""
         ptr, n = _ptr_len(buf, nbytes)
+        if self.wire == "verbs":
+            return self._verbs_reg_mr(buf, ptr + offset, n, access, mode)
         key = C.c_uint32()
         fd = C.c_int(-1)
-        m = {"direct": 0, "dmabuf": 1}[mode]
+        m = {"direct": 0, "dmabuf": 1, "peermem": 0, "auto": 0}[mode]
         N.check(self._lib.rn_reg_mr_mode(self._h, ptr + offset, n, access, m, C.byref(key), C.byref(fd)), "reg_mr")
         mr = MemoryRegion(self, ptr + offset, n, key.value, access, keepalive=buf)
         mr.dmabuf_fd = fd.value
         mr.mode = mode
         self._mrs.append(mr)
         return mr
+
+    def _verbs_reg_mr(self, buf, ptr: int, n: int, access: int, mode: str) -> MemoryRegion:
+        """``ibv_reg_dmabuf_mr`` on a dma-buf exported by the CUDA driver (``dmabuf``), or ``ibv_reg_mr`` on the pointer
+        itself (``peermem`` / ``direct``: host memory, or HBM through a peer-memory client -- nvidia-peermem or
+        ``kmod/b200p2p.ko``; the reference's whole purpose, amdp2p.c:363-371).  ``auto`` tries dma-buf first for device
+        memory and falls back to the peer-memory path."""
+        lk, rk = C.c_uint32(), C.c_uint32()
+        is_dev = self.classify((ptr, 1)) == "device"
+        order = {"auto": (["dmabuf", "peermem"] if is_dev else ["peermem"]), "dmabuf": ["dmabuf"], "peermem": ["peermem"],
+                 "direct": ["peermem"]}[mode]
+        errs = []
+        for how in order:
+            fd = -1
+            if how == "dmabuf":
+                lo, hi = ptr & ~4095, (ptr + n + 4095) & ~4095
+                cu = C.c_int(0)
+                self._lib.rn_set_device(self.device)
+                fd = self._lib.rn_dmabuf_export(lo, hi - lo, C.byref(cu))
+                if fd < 0:
+                    errs.append(f"dmabuf: export failed (CUresult {cu.value})")
+                    continue
+                h = self._lib.rn_verbs_reg_mr(self._vdev, ptr, n, 1, fd, ptr - lo, access, C.byref(lk), C.byref(rk))
+            else:
+                h = self._lib.rn_verbs_reg_mr(self._vdev, ptr, n, 0, -1, 0, access, C.byref(lk), C.byref(rk))
+            if h:
+                mr = MemoryRegion(self, ptr, n, lk.value, access, keepalive=buf, rkey=rk.value, vmr=h)
+                mr.dmabuf_fd, mr.mode = fd, how
+                self._mrs.append(mr)
+                return mr
+            if fd >= 0:
+                self._lib.rn_dmabuf_close(fd)
+            errs.append(f"{how}: {self._lib.rn_verbs_why().decode(errors='replace')}")
+        raise N.NativeError("reg_mr failed: " + "; ".join(errs))
 
     def enable_peer(self, peer_device: int):
         """Allow this context's GPU to reach ``peer_device``'s memory over NVLink (needed before
@@ -321,6 +595,13 @@ class Context:
     # ---- queues
     def create_cq(self, depth: int = 1024, mem: int = W.MEM_DEVICE) -> CompletionQueue:
         """``ibv_create_cq``; ``mem`` = ``wire.MEM_DEVICE`` (GPU pollers) or ``wire.MEM_HOST_PINNED`` (CPU pollers)."""
+        if self.wire == "verbs":
+            vc = self._lib.rn_verbs_create_cq(self._vdev, depth)
+            if not vc:
+                raise N.NativeError("ibv_create_cq failed: " + self._lib.rn_verbs_why().decode(errors="replace"))
+            cq = CompletionQueue(self, None, depth, mem, vcq=vc)
+            self._vcqs.append(cq)
+            return cq
         c = C.c_void_p()
         N.check(self._lib.rn_create_cq(self._h, depth, mem, C.byref(c)), "create_cq")
         return CompletionQueue(self, c, depth, mem)
@@ -330,25 +611,41 @@ class Context:
         """``ibv_create_qp`` (RC).  ``sq_mem`` places the rings and doorbells in device memory (posted by kernels) or pinned host memory (posted by the CPU); ``chunk_bytes`` is the engine's minimum work granule for this QP."""
         q = C.c_void_p()
         rcq = rcq or scq
+        if self.wire == "verbs":
+            vq = self._lib.rn_verbs_create_qp(self._vdev, scq._vcq, rcq._vcq, sq_depth, rq_depth)
+            if not vq:
+                raise N.NativeError("ibv_create_qp failed: " + self._lib.rn_verbs_why().decode(errors="replace"))
+            qp = VerbsQueuePair(self, vq, scq, rcq, sq_depth, rq_depth, sq_mem)
+            self._vqps.append(qp)
+            return qp
         N.check(self._lib.rn_create_qp(self._h, scq._c, rcq._c, sq_depth, rq_depth, sq_mem, chunk_bytes, C.byref(q)),
                 "create_qp")
         return QueuePair(self, q, scq, rcq, sq_depth, rq_depth, sq_mem)
 
     def loopback_qp(self, depth: int = 256, mem: int = W.MEM_DEVICE, chunk_bytes: int = 512 << 10,
-                    cq_depth: Optional[int] = None) -> QueuePair:
-        """A QP connected to itself with one CQ for sends and receives: the single-GPU wire of configs 2, 3 and 5."""
-        cq = self.create_cq(cq_depth or max(2 * depth, 64), mem)
-        return self.create_qp(cq, cq, depth, depth, mem, chunk_bytes).connect()
+                    cq_depth: Optional[int] = None, shared_cq: bool = False) -> QueuePair:
+        """A QP connected to itself: the single-GPU wire of configs 2, 3 and 5.  ``mem=MEM_DEVICE`` makes it a
+        GPU-posted QP (on the verbs wire: the mlx5 queues are handed to the GPU), ``MEM_HOST_PINNED`` a
+        host-posted one.  Send and receive completions get separate CQs unless ``shared_cq`` (a shared CQ needs
+        both of its consumers running: each leaves the other's CQEs at the head)."""
+        n = cq_depth or max(2 * depth, 64)
+        scq = self.create_cq(n, mem)
+        rcq = scq if shared_cq else self.create_cq(n, mem)
+        return self.create_qp(scq, rcq, depth, depth, mem, chunk_bytes).connect()
 
     # ---- engine
     def engine_start(self, ctas: int = 32, idle_timeout_ms: int = 5000, rnr_timeout_ms: int = 500):
         """Launch the persistent DMA engine on ``ctas`` SMs.  Allocate and register everything first: cudaMalloc, stream creation and first-time kernel loads all wait for a resident kernel.  It leaves by itself after ``idle_timeout_ms`` without work."""
+        if self.wire == "verbs":
+            return                      # the NIC is the engine
         N.check(self._lib.rn_engine_start(self._h, ctas, idle_timeout_ms, rnr_timeout_ms), "engine_start")
 
     def engine_run_oneshot(self, ctas: int = 32):
         """Launch the engine, let it execute everything already posted, return when it has
         drained and exited.  For profilers (ncu serialises kernels, so a resident engine and a
         poster can never overlap there) and for host-posted batch transfers."""
+        if self.wire == "verbs":
+            return
         self._lib.rn_engine_set_oneshot(self._h, 1)
         try:
             N.check(self._lib.rn_engine_start(self._h, ctas, 2000, 500), "engine_start")
@@ -359,6 +656,8 @@ class Context:
 
     def engine_stop(self):
         """Ask the engine to leave and wait for it; reports an engine fault as a RuntimeWarning."""
+        if self.wire == "verbs":
+            return
         N.check(self._lib.rn_engine_stop(self._h), "engine_stop")
         self._report_engine_fault()
 
@@ -395,7 +694,22 @@ class Context:
         """Stop the engine and free the HCA (queues, CQs, control arenas).  Registered tensors are untouched."""
         if not self._closed:
             self._closed = True
-            self._lib.rn_hca_close(self._h)
+            if self._vdev:
+                for q in self._vqps:
+                    q.destroy()
+                for mr in list(self._mrs):
+                    try:
+                        mr.dereg()
+                    except Exception:
+                        pass
+                for cq in self._vcqs:
+                    if cq._vcq:
+                        self._lib.rn_verbs_destroy_cq(cq._vcq)
+                        cq._vcq = None
+                self._lib.rn_verbs_close(self._vdev)
+                self._vdev = None
+            if self._h:
+                self._lib.rn_hca_close(self._h)
 
     def __enter__(self):
         return self

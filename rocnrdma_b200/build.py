@@ -31,8 +31,12 @@ CXX_SOURCES = [
     "reg/registration.cc",
     "reg/p2ptest_user.cc",
     "verbs/verbs_dl.cc",
-    "probe/probe.cc",
 ]
+# The mock rdma-core provider (csrc/mockverbs): separate shared objects with the real sonames, loaded by
+# verbs_dl.cc through ROCNRDMA_VERBS_LIBDIR exactly like the system libraries would be.
+MOCKDIR = LIBDIR / "mock"
+MOCK_VERBS = MOCKDIR / "libibverbs.so.1"
+MOCK_MLX5 = MOCKDIR / "libmlx5.so.1"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -65,18 +69,32 @@ def _stamp(paths) -> str:
 
 
 def sources():
-    cu = [CSRC / s for s in CUDA_SOURCES if (CSRC / s).exists()]
-    cc = [CSRC / s for s in CXX_SOURCES if (CSRC / s).exists()]
+    cu = [CSRC / s for s in CUDA_SOURCES]
+    cc = [CSRC / s for s in CXX_SOURCES]
+    missing = [str(p) for p in cu + cc if not p.exists()]
+    if missing:
+        raise RuntimeError(f"native sources listed in build.py do not exist: {missing}")
     return cu, cc
+
+
+def build_mock() -> Path:
+    """lib/mock/libibverbs.so.1 + libmlx5.so.1: the in-tree stand-in for rdma-core (host code only)."""
+    MOCKDIR.mkdir(parents=True, exist_ok=True)
+    subprocess.run(["g++", *CXX_FLAGS, "-I", str(CSRC), "-shared", "-Wl,-soname,libibverbs.so.1", "-o", str(MOCK_VERBS),
+                    str(CSRC / "mockverbs" / "mock_verbs.cc"), "-ldl", "-lpthread"], check=True)
+    subprocess.run(["g++", *CXX_FLAGS, "-I", str(CSRC), "-shared", "-Wl,-soname,libmlx5.so.1", "-Wl,-rpath,$ORIGIN", "-o", str(MOCK_MLX5),
+                    str(CSRC / "mockverbs" / "mock_mlx5.cc"), "-L", str(MOCKDIR), "-l:libibverbs.so.1"], check=True)
+    return MOCKDIR
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile every native source for sm_100a and link the shared object."""
     cu, cc = sources()
     headers = list(CSRC.rglob("*.h")) + list(CSRC.rglob("*.cuh"))
-    stamp = _stamp(cu + cc + headers)
+    mock_srcs = sorted((CSRC / "mockverbs").glob("*.cc"))
+    stamp = _stamp(cu + cc + headers + mock_srcs)
     stamp_file = LIBDIR / ".build_stamp"
-    if not force and LIB.exists() and stamp_file.exists() and stamp_file.read_text() == stamp:
+    if not force and LIB.exists() and MOCK_VERBS.exists() and MOCK_MLX5.exists() and stamp_file.exists() and stamp_file.read_text() == stamp:
         return LIB
     LIBDIR.mkdir(exist_ok=True)
     objdir = LIBDIR / "obj"
@@ -113,6 +131,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *map(str, objs),
             "-Xcompiler", "-fPIC", "-ldl", "-lpthread"]
     subprocess.run(link, check=True)
+    build_mock()
     stamp_file.write_text(stamp)
     return LIB
 

@@ -351,6 +351,19 @@ __device__ __forceinline__ uint8_t recv_cqe_opcode(uint8_t opc, bool err) {
   return err ? CQE_RESP_ERR : (opc == OP_SEND ? CQE_RESP_SEND : (opc == OP_SEND_IMM ? CQE_RESP_SEND_IMM : CQE_RESP_WR_IMM));
 }
 
+// CQ overrun (what a ConnectX reports as a CQ error): the producer is about to wrap onto CQEs the consumer has
+// not taken.  The consumer index is the consumer's doorbell record (be32, 24 bits) -- possibly host memory, a
+// slow read -- so it is cached in the CqDev and only refreshed when the cached value says "full".
+__device__ __forceinline__ bool cq_would_overrun(CqDev* cq, unsigned int end_pi, uint32_t log_n) {
+  const unsigned int depth = 1u << log_n;
+  unsigned int ci = *(volatile unsigned int*)&cq->ci_seen;
+  if (end_pi - ci <= depth) return false;
+  const unsigned int ci24 = be32(ld_u32_volatile(cq->dbrec)) & 0xffffffu;
+  ci = end_pi - ((end_pi - ci24) & 0xffffffu);
+  *(volatile unsigned int*)&cq->ci_seen = ci;
+  return end_pi - ci > depth;
+}
+
 __device__ __forceinline__ void retire(QpDev* qp, uint32_t lane, unsigned long long w_finished) {
   const uint32_t mask = (1u << qp->sq_log) - 1;
   const bool sys = qp->sys_scope != 0;
@@ -401,10 +414,26 @@ __device__ __forceinline__ void retire(QpDev* qp, uint32_t lane, unsigned long l
       CqDev* scq = qp->scq;
       unsigned int s_slot = 0, r_slot = 0;
       const uint32_t s_log = scq->log_n, r_log = qp->r.rcq ? qp->r.rcq->log_n : 0;
+      int over = 0;
       if (lane == 0) {
-        if (n_send) s_slot = sys ? atomicAdd_system(&scq->pi, (unsigned)n_send) : atomicAdd(&scq->pi, (unsigned)n_send);
-        if (n_recv) r_slot = atomicAdd_system(&qp->r.rcq->pi, (unsigned)n_recv);
+        if (n_send) {
+          s_slot = sys ? atomicAdd_system(&scq->pi, (unsigned)n_send) : atomicAdd(&scq->pi, (unsigned)n_send);
+          if (cq_would_overrun(scq, s_slot + (unsigned)n_send, s_log)) over |= 1;
+        }
+        if (n_recv) {
+          r_slot = atomicAdd_system(&qp->r.rcq->pi, (unsigned)n_recv);
+          // the responder's consumer record is only addressable when its CQ was not re-mapped (same process)
+          if ((qp->r.connected & 2u) && cq_would_overrun(qp->r.rcq, r_slot + (unsigned)n_recv, r_log)) over |= 2;
+        }
+        if (over) {
+          if (over & 1) atomicAdd(&scq->overruns, 1u);
+          if (over & 2) atomicAdd(&qp->r.rcq->overruns, 1u);
+          qp->state = QPS_ERR;     // CQ error is fatal for the QPs attached to it; nothing more is written to the full ring
+        }
       }
+      over = __shfl_sync(0xffffffffu, over, 0);
+      if (over & 1) want_send = false;
+      if (over & 2) want_recv = false;
       s_slot = __shfl_sync(0xffffffffu, s_slot, 0) + __popc(smask & lt);
       r_slot = __shfl_sync(0xffffffffu, r_slot, 0) + __popc(rmask & lt);
       // ---- bodies, fence, tails: every lane for its own WQE

@@ -68,7 +68,10 @@ struct Qp {
   Cq *scq, *rcq;
   Qp* peer_local = nullptr;
   uint64_t h_sq_pi = 0, h_rq_pi = 0;   // host poster indices
+  uint64_t h_sq_done = 0;              // send WQEs known complete (from polled CQEs, or the engine's retire head)
+  uint64_t h_rq_done = 0;              // receive WQEs known consumed (from polled responder CQEs)
   bool in_engine_table = false;
+  bool adopted = false;                // queues belong to a real HCA (mlx5dv): the engine never sees this QP
 };
 
 struct Hca {
@@ -477,6 +480,18 @@ RN_API int rn_poll_cq(void* cq, int max, RnWc* out) {
     out[n].qpn = v.qpn; out[n].byte_cnt = v.byte_cnt; out[n].imm = v.imm;
     out[n].wqe_counter = v.wqe_counter; out[n].opcode = v.opcode; out[n].syndrome = v.syndrome;
     out[n].wqe_opcode = v.wqe_opcode; out[n].is_error = v.is_error;
+    // flow-control credit for the host poster (rn_post_send / rn_post_recv refuse a full queue)
+    for (auto* q : h->qps) {
+      if (q->h.qpn != v.qpn) continue;
+      if (v.opcode == CQE_REQ || v.opcode == CQE_REQ_ERR) {
+        uint64_t done = q->h_sq_done + (uint16_t)(v.wqe_counter + 1 - (uint16_t)q->h_sq_done);
+        if (done <= q->h_sq_pi) q->h_sq_done = done;
+      } else if (q->rcq == c) {
+        uint64_t done = q->h_rq_done + (uint16_t)(v.wqe_counter + 1 - (uint16_t)q->h_rq_done);
+        if (done <= q->h_rq_pi) q->h_rq_done = done;
+      }
+      break;
+    }
     ++n;
     ++c->h_ci;
   }
@@ -495,7 +510,9 @@ RN_API int rn_create_qp(void* hca, void* scq, void* rcq, uint32_t nsq, uint32_t 
   std::lock_guard<std::mutex> g(h->mu);
   CU_OK(cudaSetDevice(h->dev));
   int ls = log2_exact(nsq), lr = log2_exact(nrq);
-  if (ls < 1 || ls > 15 || lr < 1 || lr > 15) return fail(-22, "create_qp: queue depths must be powers of two in [2, 32768]");
+  // 16384, not 32768: the doorbell carries a 16-bit index and the engine tells "pending" from "wrapped" by
+  // a signed 16-bit distance, so at most 2^15 - 1 WQEs may ever be outstanding.
+  if (ls < 1 || ls > 14 || lr < 1 || lr > 14) return fail(-22, "create_qp: queue depths must be powers of two in [2, 16384]");
   if (!scq || !rcq) return fail(-22, "create_qp: CQs required");
   if (h->qps.size() >= h->max_qps) return fail(-12, "create_qp: QP table full");
   if (chunk_bytes == 0) chunk_bytes = 512u << 10;
@@ -573,7 +590,8 @@ struct RnRemote {       // everything a requester needs about the responder, pre
 RN_API int rn_qp_describe(void* qp, RnRemote* out) {
   Qp* q = (Qp*)qp;
   out->rkeys = (uint64_t)q->hca->d_mkeys; out->n_rkeys = q->hca->max_mkeys; out->qpn = q->h.qpn;
-  out->rq = (uint64_t)q->h.rq; out->rq_dbr = (uint64_t)q->h.dbr; out->rq_log = q->h.rq_log; out->pad = 0;
+  out->rq = (uint64_t)q->h.rq; out->rq_dbr = (uint64_t)q->h.dbr; out->rq_log = q->h.rq_log;
+  out->pad = 1;   // flags, bit 0: pointers are in the describer's own address space (a cross-process translation clears it)
   out->rcq = (uint64_t)q->rcq->d; out->rcq_buf = (uint64_t)q->rcq->h.buf;
   return 0;
 }
@@ -588,7 +606,7 @@ RN_API int rn_qp_connect(void* qp, const RnRemote* r) {
   q->h.r.rkeys = (MKeyEntry*)r->rkeys; q->h.r.n_rkeys = r->n_rkeys; q->h.r.qpn = r->qpn;
   q->h.r.rq = (uint8_t*)r->rq; q->h.r.rq_dbr = (uint32_t*)r->rq_dbr; q->h.r.rq_log = r->rq_log;
   q->h.r.rcq = (CqDev*)r->rcq; q->h.r.rcq_buf = (uint8_t*)r->rcq_buf;
-  q->h.r.connected = 1;
+  q->h.r.connected = 1u | ((r->pad & 1u) ? 2u : 0u);   // bit 1: the responder's CQ consumer record is addressable as is
   return push(h, &q->d->r, &q->h.r, sizeof(RemoteView));
 }
 
@@ -597,6 +615,7 @@ RN_API int rn_modify_qp(void* qp, uint32_t new_state) {
   Hca* h = q->hca;
   std::lock_guard<std::mutex> g(h->mu);
   CU_OK(cudaSetDevice(h->dev));
+  if (q->adopted) return fail(-95, "modify_qp: this QP belongs to a real HCA; change its state through the verbs backend");
   uint32_t st = rn_qp_state(q);
   if (!legal_transition(st, new_state)) return fail(-22, "modify_qp: illegal transition %u -> %u", st, new_state);
   if (new_state == QPS_RTR && !q->h.r.connected) return fail(-22, "modify_qp: RTR requires a connected peer");
@@ -613,6 +632,15 @@ RN_API int rn_modify_qp(void* qp, uint32_t new_state) {
     uint32_t z[2] = {0, 0};
     if (!rc) rc = push(h, q->h.dbr, z, 8);
     if (!rc) rc = cudaMemsetAsync(q->h.resolved, 0, sizeof(Resolved) << q->h.sq_log, h->ctl) == cudaSuccess ? 0 : -5;
+    // Ready flags are generation-tagged with idx + 1 and indices restart at 0: a flag left from the previous
+    // life would make the shared submit ring the doorbell over a WQE nobody has written yet, and the stale WQE
+    // bytes (matching index and qpn) would be executed again.  Clear both.
+    if (!rc) rc = cudaMemsetAsync(q->h.ready_flags, 0, sizeof(uint32_t) << q->h.sq_log, h->ctl) == cudaSuccess ? 0 : -5;
+    if (!rc) {
+      if (q->sq_mem == MEM_HOST_PINNED) memset(q->h.sq, 0, (size_t)64 << q->h.sq_log);
+      else rc = cudaMemsetAsync(q->h.sq, 0, (size_t)64 << q->h.sq_log, h->ctl) == cudaSuccess ? 0 : -5;
+    }
+    q->h_sq_done = q->h_rq_done = 0;
     if (!rc) rc = push(h, q->d, &q->h, sizeof(QpDev));
     return rc;
   }
@@ -662,9 +690,73 @@ RN_API int rn_qp_query(void* qp, RnQpCounters* out) {
   out->n_wqe = d.n_wqe; out->n_cqe = d.n_cqe; out->n_err = d.n_err;
   out->n_db_order_violations = d.n_db_order_violations; out->n_bytes = d.n_bytes; out->n_rnr = d.n_rnr;
   out->resv_head = d.resv_head; out->ready_head = d.ready_head; out->sq_cons = d.sq_cons;
-  out->cursor = d.cursor; out->retire_head = d.retire_head;  // cursor = claim head out->state = d.state; out->pad = 0;
+  out->cursor = d.cursor; out->retire_head = d.retire_head;  // cursor = claim head
+  out->state = d.state; out->pad = 0;
   return 0;
 }
+
+// ------------------------------------------------------------------ adoption of a real HCA's queues (N3)
+// verbs_dl.cc (rn_verbs_map_qp_to_gpu) maps an mlx5 QP's send / receive rings, doorbell record, BlueFlame
+// register and completion queues into this GPU's address space; this wraps them in the QpDev / CqDev the
+// device-side poster (hca/post.cuh) already speaks, so rdma_stream_kernel, pack_fp8_write_kernel and the
+// GEMM epilogue drive a ConnectX with the code that drives the software HCA.  What differs from a softhca QP:
+//   * every ring lives outside the GPU (host memory the NIC reads over PCIe; the register is MMIO), so
+//     sq_in_device = 0 and the poster's doorbell release is system scope;
+//   * geometry comes from the provider: wqe_cnt / cqe_cnt are powers of two but not ours to choose;
+//   * the engine never sees the QP (no MKey table, no resolved[] slots): the NIC executes the WQEs.
+// The QP must be fresh (nothing posted or polled through libibverbs): the producer / consumer indices start
+// at 0 here, as they do in the hardware.
+struct RnGpuQp {
+  uint64_t sq_dev, rq_dev, dbrec_dev, bf_dev, cq_dev, cq_dbrec_dev, rcq_dev, rcq_dbrec_dev;
+  uint32_t sq_wqe_cnt, rq_wqe_cnt, cq_cqe_cnt, rcq_cqe_cnt, qpn, cqn, rcqn, flags;
+};
+RN_API int rn_qp_adopt(void* hca, const RnGpuQp* g, void** out) {
+  Hca* h = (Hca*)hca;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CU_OK(cudaSetDevice(h->dev));
+  const int ls = log2_exact(g->sq_wqe_cnt), lr = log2_exact(g->rq_wqe_cnt), lc = log2_exact(g->cq_cqe_cnt), lrc = log2_exact(g->rcq_cqe_cnt);
+  if (ls < 0 || lr < 0 || lc < 0 || lrc < 0) return fail(-22, "adopt: queue sizes must be powers of two (sq %u rq %u cq %u rcq %u)",
+                                                         g->sq_wqe_cnt, g->rq_wqe_cnt, g->cq_cqe_cnt, g->rcq_cqe_cnt);
+  if (ls > 15) return fail(-22, "adopt: send queue of %u WQEBBs exceeds the 16-bit doorbell window", g->sq_wqe_cnt);
+  if (!g->sq_dev || !g->dbrec_dev || !g->bf_dev || !g->cq_dev || !g->cq_dbrec_dev) return fail(-22, "adopt: unmapped queue");
+  auto make_cq = [&](uint64_t buf, uint64_t dbrec, int lg, uint32_t cqn) -> Cq* {
+    Cq* c = new Cq();
+    c->hca = h; c->mem = MEM_HOST_PINNED; c->ring_host = nullptr;     // polled on the device, never by rn_poll_cq
+    c->d = (CqDev*)arena_alloc(h, sizeof(CqDev), false);
+    if (!c->d) { delete c; return nullptr; }
+    memset(&c->h, 0, sizeof c->h);
+    c->h.buf = (uint8_t*)buf; c->h.dbrec = (uint32_t*)dbrec; c->h.log_n = (uint32_t)lg; c->h.cqn = cqn;
+    if (push(h, c->d, &c->h, sizeof(CqDev))) { delete c; return nullptr; }
+    h->cqs.push_back(c);
+    return c;
+  };
+  Cq* scq = make_cq(g->cq_dev, g->cq_dbrec_dev, lc, g->cqn);
+  Cq* rcq = (g->rcq_dev && g->rcq_dev != g->cq_dev) ? make_cq(g->rcq_dev, g->rcq_dbrec_dev, lrc, g->rcqn) : scq;
+  if (!scq || !rcq) return fail(-12, "adopt: control arena exhausted");
+  Qp* q = new Qp();
+  q->hca = h; q->sq_mem = MEM_HOST_PINNED; q->scq = scq; q->rcq = rcq; q->adopted = true;
+  const uint32_t nsq = g->sq_wqe_cnt;
+  unsigned long long* trace = (unsigned long long*)arena_alloc(h, (size_t)nsq * 64, false);
+  uint32_t* flags = (uint32_t*)arena_alloc(h, (size_t)nsq * 4, false);
+  q->d = (QpDev*)arena_alloc(h, sizeof(QpDev), false);
+  if (!trace || !flags || !q->d) { delete q; return fail(-12, "adopt: control arena exhausted"); }
+  memset(&q->h, 0, sizeof q->h);
+  q->h.qpn = g->qpn;
+  q->h.state = QPS_RTS;
+  q->h.sq = (uint8_t*)g->sq_dev; q->h.sq_log = (uint32_t)ls;
+  q->h.rq = (uint8_t*)g->rq_dev; q->h.rq_log = (uint32_t)lr;
+  q->h.dbr = (uint32_t*)g->dbrec_dev; q->h.bf = (unsigned long long*)g->bf_dev;
+  q->h.scq = scq->d; q->h.rcq = rcq->d;
+  q->h.lkeys = nullptr; q->h.n_lkeys = 0; q->h.chunk_bytes = 0;
+  q->h.sys_scope = 1; q->h.sq_in_device = 0;
+  q->h.trace = trace; q->h.ready_flags = flags; q->h.resolved = nullptr;
+  int rc = push(h, q->d, &q->h, sizeof(QpDev));
+  if (rc) { delete q; return rc; }
+  h->qps.push_back(q);
+  *out = q;
+  return 0;
+}
+RN_API int rn_qp_is_adopted(void* qp) { return ((Qp*)qp)->adopted ? 1 : 0; }
 
 // ------------------------------------------------------------------ host-posted verbs
 static int host_store(Qp* q, void* dst, const void* src, size_t n) {
@@ -675,8 +767,18 @@ static int host_store(Qp* q, void* dst, const void* src, size_t n) {
 RN_API int rn_post_send(void* qp, uint32_t opcode, uint64_t laddr, uint32_t lkey, uint64_t raddr, uint32_t rkey,
                         uint32_t bytes, uint32_t flags, uint32_t imm, uint64_t* idx_out) {
   Qp* q = (Qp*)qp;
+  if (q->adopted) return fail(-95, "post_send: adopted QPs are posted to by device kernels only");
   cudaSetDevice(q->hca->dev);
   uint64_t idx = q->h_sq_pi;
+  const uint64_t depth = 1ull << q->h.sq_log;
+  if (idx - q->h_sq_done >= depth) {
+    // Unsignaled WQEs produce no CQE: before refusing, ask the engine how far it has retired.
+    unsigned long long rh = 0;
+    if (!pull(q->hca, &rh, &q->d->retire_head, 8) && rh > q->h_sq_done && rh <= idx) q->h_sq_done = rh;
+    if (idx - q->h_sq_done >= depth)
+      return fail(-12, "post_send: send queue full (%llu posted, %llu complete, depth %llu): poll the CQ first",
+                  (unsigned long long)idx, (unsigned long long)q->h_sq_done, (unsigned long long)depth);
+  }
   Wqe64 w;
   memset(&w, 0, sizeof w);
   switch (opcode) {
@@ -713,6 +815,17 @@ RN_API int rn_post_recv(void* qp, uint64_t addr, uint32_t lkey, uint32_t bytes) 
   Qp* q = (Qp*)qp;
   cudaSetDevice(q->hca->dev);
   uint64_t i = q->h_rq_pi;
+  if (i - q->h_rq_done >= (1ull << q->h.rq_log)) {
+    // Consumption is only visible to the host through polled responder CQEs; when a kernel consumes the
+    // receive CQ instead, ask the requester's engine state (possible when the peer QP is in this process).
+    unsigned long long taken = 0;
+    if (q->peer_local && !pull(q->hca, &taken, &q->peer_local->d->rq_head, 8) && taken > q->h_rq_done && taken <= i)
+      q->h_rq_done = taken;
+    const bool can_know = q->peer_local || q->rcq->ring_host;
+    if (can_know && i - q->h_rq_done >= (1ull << q->h.rq_log))
+      return fail(-12, "post_recv: receive queue full (%llu posted, %llu consumed): poll the receive CQ first",
+                  (unsigned long long)i, (unsigned long long)q->h_rq_done);
+  }
   RecvWqe w;
   encode_data(&w.data, addr, lkey, bytes);
   int rc = host_store(q, q->h.rq + ((i & ((1ull << q->h.rq_log) - 1)) << 4), &w, 16);

@@ -53,8 +53,8 @@ struct CqDev {
   uint32_t cqn;
   unsigned int pi;           // producer index, claimed by engines with atomicAdd (system scope)
   unsigned int ci;           // device consumer index (device pollers)
-  unsigned int overruns;
-  unsigned int pad;
+  unsigned int overruns;     // completions that found the ring full of unconsumed CQEs (the QP that hit it goes to ERR)
+  unsigned int ci_seen;      // consumer index as last read from dbrec by a producer (refreshed only when the ring looks full)
 };
 
 // Per-SQ-slot record written by the WQE prologue (address translation, checks)
@@ -81,7 +81,7 @@ struct RemoteView {
   uint8_t* rq;                // responder receive ring (16-byte RecvWqe strides)
   uint32_t* rq_dbr;           // responder doorbell record ([DBR_RCV] = be32 count)
   uint32_t rq_log;
-  uint32_t connected;
+  uint32_t connected;         // bit 0: connected; bit 1: responder CQ's consumer record addressable (same process)
   CqDev* rcq;                 // responder's receive CQ
   uint8_t* rcq_buf;           // its ring, translated
 };

@@ -61,6 +61,7 @@ struct GemmArgs {
   uint64_t remote_va;
   uint32_t signal_every;
   uint32_t with_imm;         // 1: RDMA_WRITE_IMM, immediate = panel index (wakes a consumer on the receiving GPU)
+  uint32_t post_only;        // 1: post panels + flush but do not wait for the drain (profilers serialise kernels; see pack_fp8.cu)
   uint32_t out_fp8;          // 1: epilogue emits block-scaled fp8 panel records instead of bf16 rows (see below)
   uint32_t dense_probe;      // link probe ONLY (output layout is wrong on purpose): every 32x64 box lands as one contiguous 4 KiB run
   uint32_t plain_stores;     // 1: bf16 epilogue writes rows with per-thread 16-byte stores instead of staged TMA stores (A/B switch)
@@ -418,7 +419,7 @@ gemm_send_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           st_v4(slot + 16, 0u, 0u, 0u, 0u);
           st_v4(slot + 32, 0u, 0u, 0u, 0u);
           st_v4(slot + 48, 0u, 0u, 0u, 0u);
-          if (sq_submit(g.qp, fidx, 1, g.timeout_ns, true) == WAIT_OK) rc = sq_wait(g.qp, fidx, g.timeout_ns);
+          if (sq_submit(g.qp, fidx, 1, g.timeout_ns, true) == WAIT_OK) rc = g.post_only ? WAIT_OK : sq_wait(g.qp, fidx, g.timeout_ns);
         }
         if (posted != m_blks && rc == WAIT_OK) rc = WAIT_TIMEOUT;
         if (rc != WAIT_OK) g.out[0] = (unsigned long long)(long long)rc;
@@ -669,7 +670,7 @@ gemm_send2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           uint8_t* slot = g.qp->sq + ((fidx & ((1ull << g.qp->sq_log) - 1)) << 6);
           st_v4(slot + 0, ctrl_word0(OP_NOP, (uint16_t)fidx), ctrl_word1(g.qp->qpn, 1), (uint32_t)CTRL_CQ_UPDATE << 24, 0u);
           st_v4(slot + 16, 0u, 0u, 0u, 0u); st_v4(slot + 32, 0u, 0u, 0u, 0u); st_v4(slot + 48, 0u, 0u, 0u, 0u);
-          if (sq_submit(g.qp, fidx, 1, g.timeout_ns, true) == WAIT_OK) rc = sq_wait(g.qp, fidx, g.timeout_ns);
+          if (sq_submit(g.qp, fidx, 1, g.timeout_ns, true) == WAIT_OK) rc = g.post_only ? WAIT_OK : sq_wait(g.qp, fidx, g.timeout_ns);
         }
         if (posted != g.M / BM && rc == WAIT_OK) rc = WAIT_TIMEOUT;
         if (rc != WAIT_OK) g.out[0] = (unsigned long long)(long long)rc;
@@ -730,7 +731,7 @@ RN_API int rn_k_gemm_send(uint64_t stream, int grid, uint64_t a, uint64_t b, uin
   if (rc) return rc;
   GemmArgs g;
   g.c = (__nv_bfloat16*)c; g.M = M; g.N = N; g.K = K; g.qp = (QpDev*)qp_dev; g.c_va = c_va; g.lkey = lkey; g.rkey = rkey;
-  g.remote_va = remote_va; g.signal_every = signal_every ? signal_every : 1; g.with_imm = with_imm; g.out_fp8 = out_fp8; g.group_m = group_m ? group_m : 1;
+  g.remote_va = remote_va; g.signal_every = signal_every ? signal_every : 1; g.with_imm = with_imm & 1u; g.post_only = (with_imm >> 1) & 1u; g.out_fp8 = out_fp8; g.group_m = group_m ? group_m : 1;
   g.direct = (flags & kFlagDirect) ? 1 : 0; g.plain_stores = (flags & kFlagPlainStores) ? 1 : 0; g.dense_probe = (flags & kFlagDenseProbe) ? 1 : 0;
   const uint32_t m_blks = M / BM;
   g.counters = (unsigned int*)counters_dev;

@@ -53,6 +53,9 @@ struct PackArgs {
   uint32_t rkey;
   uint64_t remote_va;        // destination of record 0; records keep their stride remotely
   uint32_t with_imm;         // 1: RDMA_WRITE_IMM carrying the chunk id (wakes a device consumer)
+  uint32_t post_only;        // 1: post everything (incl. the flush) but do not wait for the wire to drain -- for profilers that
+                             //    serialise kernels (the NIC / engine cannot run while this kernel is resident) and for callers
+                             //    that overlap the drain with other work and reap the flush CQE later
   uint32_t signal_every;     // CQE every k-th chunk (the last one is always signaled)
   unsigned int* counters;    // [0..n_chunks): tiles done per chunk ; [n_chunks]: CTAs done
   unsigned long long* acc;   // device accumulators: [0] max WQE index+1, [1] WQEs posted, [2] ~first post time
@@ -175,7 +178,7 @@ __global__ void __launch_bounds__(kPackThreads) pack_fp8_write_kernel(PackArgs a
         st_v4(slot + 16, 0u, 0u, 0u, 0u);
         st_v4(slot + 32, 0u, 0u, 0u, 0u);
         st_v4(slot + 48, 0u, 0u, 0u, 0u);
-        if (sq_submit(a.qp, fidx, 1, a.timeout_ns, /*shared=*/true) == WAIT_OK) rc = sq_wait(a.qp, fidx, a.timeout_ns);
+        if (sq_submit(a.qp, fidx, 1, a.timeout_ns, /*shared=*/true) == WAIT_OK) rc = a.post_only ? WAIT_OK : sq_wait(a.qp, fidx, a.timeout_ns);
       }
       if (posted != a.n_chunks && rc == WAIT_OK) rc = WAIT_TIMEOUT;
       if (rc != WAIT_OK) a.out[0] = (unsigned long long)(long long)rc;
@@ -285,7 +288,7 @@ RN_API int rn_k_pack_fp8_write(uint64_t stream, int grid, uint64_t src, uint64_t
   PackArgs a;
   a.src = (const __nv_bfloat16*)src; a.staging = (uint8_t*)staging; a.n_elems = n_elems; a.chunk_elems = chunk_elems;
   a.n_chunks = (uint32_t)(n_elems / chunk_elems); a.qp = (QpDev*)qp_dev; a.staging_va = staging_va; a.lkey = lkey;
-  a.rkey = rkey; a.remote_va = remote_va; a.with_imm = with_imm; a.signal_every = signal_every ? signal_every : 1;
+  a.rkey = rkey; a.remote_va = remote_va; a.with_imm = with_imm & 1u; a.post_only = (with_imm >> 1) & 1u; a.signal_every = signal_every ? signal_every : 1;
   a.counters = (unsigned int*)counters_dev;
   a.acc = (unsigned long long*)(counters_dev + (((uint64_t)a.n_chunks + 1) * 4 + 7) / 8 * 8);
   a.out = (unsigned long long*)out_dev;

@@ -30,6 +30,8 @@ struct StreamArgs {
   uint32_t window;         // max outstanding WQEs per QP
   uint32_t signal_every;   // 1 = every WQE signaled
   uint32_t burst;          // WQEs per doorbell (1..32)
+  uint32_t post_only;      // 1: do not wait for the last completion (the caller reaps it: profilers serialise kernels, so the
+                           //    engine / NIC cannot make progress while this kernel is resident)
   uint64_t slot_stride;    // each iteration i uses offset (i % nslots) * slot_stride
   uint32_t nslots;
   uint64_t timeout_ns;
@@ -50,15 +52,19 @@ __global__ void __launch_bounds__(32, 1) rdma_stream_kernel(StreamArgs a) {
   int status = WAIT_OK;
   unsigned long long first = ~0ull, last = 0;
   uint32_t done = 0;
+  // The warp owns this QP and its send CQ for the whole kernel: queue state lives in lane 0's registers
+  // (dev::Poster), no atomics, the CQ is only read when the window is full.
+  Poster p = poster_open(qp);
+  if (qp->state == QPS_ERR) status = WAIT_QP_ERROR;
   const unsigned long long t0 = globaltimer_ns();
-  while (done < a.iters) {
+  while (done < a.iters && status != WAIT_QP_ERROR) {
     const uint32_t n = min(a.burst, a.iters - done);
     unsigned long long idx = 0;
     int rc = WAIT_OK;
     if (lane == 0) {
-      if (a.window && done + n > a.window) rc = sq_wait(qp, last + n - a.window, a.timeout_ns);   // leaves <= window - n outstanding
+      if (a.window && done + n > a.window) rc = poster_wait(p, last + n - a.window, a.timeout_ns);   // leaves <= window - n outstanding
       if (rc != WAIT_TIMEOUT) {
-        idx = sq_reserve(qp, n, a.timeout_ns);
+        idx = poster_reserve(p, n, a.timeout_ns);
         if (idx == ~0ull) rc = WAIT_TIMEOUT;
       }
     }
@@ -73,25 +79,25 @@ __global__ void __launch_bounds__(32, 1) rdma_stream_kernel(StreamArgs a) {
       const bool sig = (a.signal_every <= 1) || ((i + 1) % a.signal_every == 0) || (i + 1 == a.iters);
       const uint8_t flags = sig ? CTRL_CQ_UPDATE : 0;
       if (a.opcode == OP_SEND)
-        write_send_wqe(qp, idx + lane, OP_SEND, lbase + off, a.lkey, a.bytes, flags);
+        poster_build_send(p, idx + lane, OP_SEND, lbase + off, a.lkey, a.bytes, flags);
       else
-        write_rdma_wqe(qp, idx + lane, (uint8_t)a.opcode, lbase + off, a.lkey, rbase + off, a.rkey, a.bytes, flags);
-      if (lane) trace_stamp(qp, idx + lane, TR_POST);
+        poster_build_rdma(p, idx + lane, (uint8_t)a.opcode, lbase + off, a.lkey, rbase + off, a.rkey, a.bytes, flags);
     }
-    __syncwarp();                                    // the burst's WQE bytes happen-before lane 0's release fence
-    if (lane == 0) sq_submit(qp, idx, n, a.timeout_ns, /*shared=*/false);
+    if (n > 1) __syncwarp();                         // the burst's WQE bytes happen-before lane 0's release
+    if (lane == 0) poster_ring(p, idx + n);
     last = idx + n - 1;
     done += n;
   }
   if (lane != 0) return;
-  if (done) {
-    int rc = sq_wait(qp, last, a.timeout_ns);
+  if (done && !a.post_only) {
+    int rc = poster_wait(p, last, a.timeout_ns);
     if (rc != WAIT_OK) status = rc;
   }
   const unsigned long long t1 = globaltimer_ns();
+  poster_close(p);
   out[0] = (unsigned long long)(long long)status;
   out[1] = t0; out[2] = t1; out[3] = done; out[4] = first; out[5] = last;
-  out[6] = ld_u64_volatile(&qp->sq_cons);
+  out[6] = p.cons;
   out[7] = 0;
 }
 
@@ -114,6 +120,7 @@ RN_API int rn_k_rdma_stream(uint64_t stream, const uint64_t* qps_host, uint32_t 
   StreamArgs a;
   if (nqp == 0 || nqp > (uint32_t)kMaxStreamQps) return -22;
   for (uint32_t i = 0; i < nqp; ++i) a.qps[i] = (QpDev*)qps_host[i];
+  a.post_only = (opcode >> 31) & 1u; opcode &= 0x7fffffffu;
   a.opcode = opcode; a.laddr = laddr; a.raddr = raddr; a.stride = stride;
   a.lkey = lkey; a.rkey = rkey; a.bytes = bytes; a.iters = iters; a.window = window;
   rn_stream_clamp(window, &burst, &signal_every);

@@ -60,7 +60,7 @@ def _parse(view, n_elems, wire) -> PackResult:
 
 def pack_fp8_write(ctx, src: torch.Tensor, staging_mr, qp=None, dst_mr=None, chunk_elems: int = 1 << 20,
                    with_imm: bool = False, signal_every: int = 1, grid: int = 0, timeout_ms: int = 2000,
-                   stream=None, sync: bool = True, scratch_slot: int = 0):
+                   stream=None, sync: bool = True, scratch_slot: int = 0, post_only: bool = False):
     """Pack ``src`` (bf16) into fp8 chunk records in ``staging_mr`` and, if ``qp`` is given,
     RDMA-write every record to the same offset of ``dst_mr`` from inside the kernel."""
     assert src.dtype == torch.bfloat16 and src.is_contiguous()
@@ -78,7 +78,7 @@ def pack_fp8_write(ctx, src: torch.Tensor, staging_mr, qp=None, dst_mr=None, chu
     rc = lib.rn_k_pack_fp8_write(_stream_ptr(ws), grid, src.data_ptr(), staging_mr.addr, n, chunk_elems,
                                  qp.dev_ptr if qp is not None else 0, staging_mr.addr, staging_mr.lkey,
                                  dst_mr.addr if dst_mr is not None else 0, dst_mr.rkey if dst_mr is not None else 0,
-                                 int(with_imm), signal_every, counters, out_addr, timeout_ms)
+                                 int(with_imm) | (2 if post_only else 0), signal_every, counters, out_addr, timeout_ms)
     if rc:
         raise N.NativeError(f"pack_fp8_write launch failed ({rc})")
     if not sync:

@@ -56,14 +56,15 @@ class StreamResult:
 
 def rdma_stream(qps, opcode: int, src_mr, dst_mr, nbytes: int, iters: int = 1, window: int = 0,
                 signal_every: int = 1, burst: int = 1, stride: int = 0, slot_stride: int = 0, nslots: int = 1,
-                timeout_ms: int = 2000, stream=None, sync: bool = True, out=None):
+                timeout_ms: int = 2000, stream=None, sync: bool = True, out=None, post_only: bool = False):
     """Launch the device poster: one CTA per QP posts ``iters`` work requests of
     ``nbytes`` (window-limited), polls its CQ on the device and returns device times.
     ``burst`` work requests share one slot reservation and one doorbell (perftest ``--post_list``),
     ``signal_every`` is the CQ moderation (``--cq-mod``); both are clamped so the window can always drain.
 
     For RDMA_READ ``src_mr`` is the local destination and ``dst_mr`` the remote source,
-    mirroring the laddr/raddr roles in the WQE.
+    mirroring the laddr/raddr roles in the WQE.  ``post_only`` skips the final completion wait (``iters`` must fit
+    the window): the work is reaped later -- by ``Context.engine_run_oneshot`` under a profiler, or by the caller.
     """
     lib = N.load()
     if not isinstance(qps, (list, tuple)):
@@ -73,7 +74,7 @@ def rdma_stream(qps, opcode: int, src_mr, dst_mr, nbytes: int, iters: int = 1, w
     nq = len(qps)
     qp_arr = (C.c_uint64 * nq)(*[q.dev_ptr for q in qps])
     out_addr, out_view = ctx.scratch(nq * 64) if out is None else out
-    rc = lib.rn_k_rdma_stream(_stream_ptr(ws), qp_arr, nq, opcode, src_mr.addr, src_mr.lkey,
+    rc = lib.rn_k_rdma_stream(_stream_ptr(ws), qp_arr, nq, opcode | (0x80000000 if post_only else 0), src_mr.addr, src_mr.lkey,
                               dst_mr.addr if dst_mr is not None else 0, dst_mr.rkey if dst_mr is not None else 0,
                               stride, nbytes, iters, window, signal_every, burst, slot_stride, nslots, timeout_ms, out_addr)
     if rc:

@@ -3,7 +3,32 @@ import sys
 
 import pytest
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+# The ConnectX backend dlopen()s libibverbs once per process: point it at the in-tree mock provider before
+# anything loads it (no rdma-core in the image, no /dev/infiniband in the sandbox).  `wire="auto"` never
+# selects the mock, so the softhca tests are unaffected.
+os.environ.setdefault("ROCNRDMA_VERBS_LIBDIR", os.path.join(ROOT, "rocnrdma_b200", "lib", "mock"))
+
+
+def _private_kmod_sim():
+    """The mock's peer-memory bridge gets its OWN copy of the kmod simulation: test_kmod_sim.py resets and
+    reloads the shared one freely, and a dlopen of the same path would share its globals."""
+    import shutil
+    import tempfile
+    try:
+        from tools import build_kmod_sim
+        src = build_kmod_sim.build()
+    except Exception:
+        return
+    d = tempfile.mkdtemp(prefix="rn_kmod_sim_")
+    dst = os.path.join(d, "libb200p2p_sim_bridge.so")
+    shutil.copy(src, dst)
+    os.environ.setdefault("ROCNRDMA_KMOD_SIM", dst)
+
+
+_private_kmod_sim()
 
 
 def pytest_configure(config):

@@ -83,10 +83,19 @@ def test_probe_on_a_fake_gpu_box(tmp_path, monkeypatch):
 
 
 def test_verbs_backend_reports_why_it_is_off():
-    from rocnrdma_b200 import _native as N
-    import ctypes as C
-    lib = N.load()
-    lib.rn_verbs_available.restype = C.c_int
-    lib.rn_verbs_why.restype = C.c_char_p
-    assert lib.rn_verbs_available() == 0                      # no NIC path in this image
-    assert b"infiniband" in lib.rn_verbs_why().lower() or b"ibverbs" in lib.rn_verbs_why().lower()
+    """Without the mock (a fresh process with ROCNRDMA_VERBS_LIBDIR unset) the backend looks for the system's
+    rdma-core, finds none in this image, says so -- and `wire="auto"` falls back to the software HCA."""
+    import os
+    import subprocess
+    import sys
+    env = {k: v for k, v in os.environ.items() if k not in ("ROCNRDMA_VERBS_LIBDIR", "ROCNRDMA_WIRE")}
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from rocnrdma_b200 import _native as N, api\n"
+            "lib = N.load()\n"
+            "print(lib.rn_verbs_compiled(), lib.rn_verbs_available(), lib.rn_verbs_is_mock(), api.resolve_wire('auto'))\n"
+            "print(lib.rn_verbs_why().decode())\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    first, why = out.stdout.strip().split("\n", 1)
+    assert first == "1 0 0 softhca"                            # compiled in, nothing usable, not the mock
+    assert "infiniband" in why.lower() or "ibverbs" in why.lower()
