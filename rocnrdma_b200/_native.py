@@ -233,11 +233,21 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    if not _LIB_PATH.exists():
-        if os.environ.get("ROCNRDMA_NO_AUTOBUILD"):
+    if os.environ.get("ROCNRDMA_NO_AUTOBUILD"):
+        if not _LIB_PATH.exists():
             raise NativeError(f"{_LIB_PATH} not built; run `python -m rocnrdma_b200.build`")
-        from . import build as _build
-        _build.build()
+    else:
+        # build() is a content-hash check when the library is current (milliseconds); a library older than its
+        # sources is rebuilt rather than silently used (an edited kernel that is not the one running is the
+        # worst kind of test result).
+        try:
+            from . import build as _build
+            _build.build()
+        except Exception as e:
+            if not _LIB_PATH.exists():
+                raise NativeError(f"{_LIB_PATH} is missing and could not be built: {e}") from e
+            import warnings
+            warnings.warn(f"rocnrdma_b200: could not verify that {_LIB_PATH.name} is current ({e}); using it as is", RuntimeWarning)
     # NOTE: do not set CUDA_MODULE_LOADING=EAGER here.  It would make the driver load every
     # kernel of every library in the process (torch ships GBs of them) -- minutes on a cold
     # box.  rn_hca_open preloads *our* kernels explicitly instead.
