@@ -34,6 +34,7 @@
 #include <linux/mm.h>
 #include <linux/errno.h>
 
+#include <linux/kref.h>
 #include "nv-p2p.h"
 #include "b200p2ptest.h"
 
@@ -57,14 +58,26 @@ struct b200p2ptest_node {
 	u64 va;
 	u64 size;
 	int revoked;
+	int zombie; /* PUT_PAGES / close lost a race with a revoke: the free callback, still to come, frees the node */
 	struct nvidia_p2p_page_table *page_table;
 };
 
+/* Per-open-file state.  Reference counted: the file holds one reference, every free callback that is running
+ * holds one, so close() can never free the list (and its mutex) under a callback that is still inside it. */
 struct b200p2ptest_list {
 	struct list_head head;
 	struct mutex lock;
+	struct kref ref;
 	u64 next_handle;
 };
+
+static void b200p2ptest_list_free(struct kref *ref)
+{
+	struct b200p2ptest_list *list = container_of(ref, struct b200p2ptest_list, ref);
+
+	mutex_destroy(&list->lock);
+	kfree(list);
+}
 
 static unsigned long node_page_size(const struct b200p2ptest_node *n)
 {
@@ -80,19 +93,32 @@ static unsigned long node_page_size(const struct b200p2ptest_node *n)
 static void b200p2ptest_free_callback(void *data)
 {
 	struct b200p2ptest_node *node = data;
+	struct b200p2ptest_list *list;
 	struct nvidia_p2p_page_table *pt;
+	int zombie;
 
 	if (!node)
 		return;
+	/* a callback only fires for a pin that exists, i.e. a node that has not been put yet: node and list are
+	 * alive here; the reference keeps the list so past the point where the node may be freed */
+	list = node->owner;
+	kref_get(&list->ref);
 	MSG_ERR("free callback: va 0x%llx size 0x%llx was revoked by the GPU driver\n",
 		(unsigned long long)node->va, (unsigned long long)node->size);
-	mutex_lock(&node->owner->lock);
+	mutex_lock(&list->lock);
 	node->revoked = 1;
 	pt = node->page_table;
 	node->page_table = NULL;
-	mutex_unlock(&node->owner->lock);
+	zombie = node->zombie;
+	mutex_unlock(&list->lock);
+	/* a live node may be freed by a racing PUT_PAGES / close from here on; a zombie is ours alone */
 	if (pt)
 		nvidia_p2p_free_page_table(pt); /* never put_pages after a revoke */
+	if (zombie) {
+		kfree(node);
+		kref_put(&list->ref, b200p2ptest_list_free); /* the reference the zombie held */
+	}
+	kref_put(&list->ref, b200p2ptest_list_free);
 }
 
 static int b200p2ptest_open(struct inode *inode, struct file *filp)
@@ -103,8 +129,10 @@ static int b200p2ptest_open(struct inode *inode, struct file *filp)
 		return -ENOMEM;
 	INIT_LIST_HEAD(&list->head);
 	mutex_init(&list->lock);
+	kref_init(&list->ref);
 	list->next_handle = 1;
 	filp->private_data = list;
+	MSG_INFO("open: session %p\n", list);
 	return 0;
 }
 
@@ -137,8 +165,29 @@ static int drop_nodes(struct b200p2ptest_list *list, int match, u64 va, u64 size
 		if (pt && !revoked) {
 			int ret = nvidia_p2p_put_pages(0, 0, node->va, pt);
 
-			if (ret)
-				MSG_ERR("put_pages(0x%llx) failed: %d\n", (unsigned long long)node->va, ret);
+			if (ret) {
+				/* Refused: a revoke of this pin is in flight.  If its callback has already been here it
+				 * found the page table taken, so releasing it falls to us; if it is still to come, the
+				 * node (and a reference on the list it points to) must outlive this call: hand both,
+				 * and the page table, to the callback. */
+				int handed_over = 0;
+
+				MSG_ERR("put_pages(0x%llx) failed: %d (revoked meanwhile)\n", (unsigned long long)node->va, ret);
+				mutex_lock(&list->lock);
+				if (!node->revoked) {
+					list_del(&node->list_node); /* off our private list BEFORE the callback may free it */
+					node->page_table = pt;
+					node->zombie = 1;
+					kref_get(&list->ref);
+					handed_over = 1;
+				}
+				mutex_unlock(&list->lock);
+				if (handed_over) {
+					++n; /* node is the callback's from here on: not touched again */
+					continue;
+				}
+				nvidia_p2p_free_page_table(pt);
+			}
 		}
 		list_del(&node->list_node);
 		kfree(node);
@@ -155,11 +204,9 @@ static int b200p2ptest_release(struct inode *inode, struct file *filp)
 	if (!list)
 		return 0;
 	n = drop_nodes(list, 0, 0, 0);
-	if (n)
-		MSG_INFO("close: released %d pin(s) the application left behind\n", n);
-	mutex_destroy(&list->lock);
-	kfree(list);
+	MSG_INFO("close: session %p, released %d pin(s) the application left behind\n", list, n);
 	filp->private_data = NULL;
+	kref_put(&list->ref, b200p2ptest_list_free); /* a free callback still inside the list keeps it alive */
 	return 0;
 }
 
@@ -194,6 +241,7 @@ static long ioctl_is_gpu_address(struct file *filp, unsigned long arg)
 		return -EFAULT;
 	p.ret_value = probe_gpu_page(p.addr);
 	p.reserved = 0;
+	MSG_INFO("IS_GPU_ADDRESS: addr 0x%llx -> %u\n", (unsigned long long)p.addr, p.ret_value);
 	if (copy_to_user((void __user *)arg, &p, sizeof(p)))
 		return -EFAULT;
 	return 0;
@@ -205,6 +253,7 @@ static long ioctl_get_page_size(struct file *filp, unsigned long arg)
 
 	if (copy_from_user(&p, (void __user *)arg, sizeof(p)))
 		return -EFAULT;
+	MSG_INFO("GET_PAGE_SIZE: addr 0x%llx length 0x%llx\n", (unsigned long long)p.addr, (unsigned long long)p.length);
 	if (!p.length || !probe_gpu_page(p.addr) || !probe_gpu_page(p.addr + p.length - 1))
 		return -EFAULT; /* same errno the reference returns when the GPU driver refuses */
 	p.page_size = B200P2P_GPU_PAGE_SIZE;
@@ -218,10 +267,12 @@ static long ioctl_get_pages(struct file *filp, unsigned long arg)
 	struct b200p2ptest_list *list = filp->private_data;
 	struct b200p2p_get_pages p;
 	struct b200p2ptest_node *node;
+	struct nvidia_p2p_page_table *pt = NULL, *dead = NULL;
 	int ret;
 
 	if (copy_from_user(&p, (void __user *)arg, sizeof(p)))
 		return -EFAULT;
+	MSG_INFO("GET_PAGES: addr 0x%llx length 0x%llx\n", (unsigned long long)p.addr, (unsigned long long)p.length);
 	if (!p.length || (p.addr & (B200P2P_GPU_PAGE_SIZE - 1)) || (p.length & (B200P2P_GPU_PAGE_SIZE - 1)))
 		return -EINVAL;
 	node = kzalloc(sizeof(*node), GFP_KERNEL);
@@ -236,17 +287,28 @@ static long ioctl_get_pages(struct file *filp, unsigned long arg)
 	list_add(&node->list_node, &list->head);
 	mutex_unlock(&list->lock);
 
-	ret = nvidia_p2p_get_pages(0, 0, p.addr, p.length, &node->page_table, b200p2ptest_free_callback, node);
-	if (ret || (!node->page_table && !node->revoked)) {
+	ret = nvidia_p2p_get_pages(0, 0, p.addr, p.length, &pt, b200p2ptest_free_callback, node);
+	if (ret || !pt) {
 		mutex_lock(&list->lock);
 		list_del(&node->list_node);
 		mutex_unlock(&list->lock);
 		kfree(node);
 		return ret ? -EFAULT : -EINVAL;
 	}
+	/* publish the pin under the lock the free callback takes: it may already have fired (the memory was freed
+	 * the instant it was pinned), in which case it found no page table to release and that falls to us */
+	mutex_lock(&list->lock);
+	if (node->revoked) {
+		dead = pt;
+	} else {
+		node->page_table = pt;
+	}
 	p.handle = node->handle;
 	p.entries = node->page_table ? node->page_table->entries : 0;
 	p.page_size = (u32)node_page_size(node);
+	mutex_unlock(&list->lock);
+	if (dead)
+		nvidia_p2p_free_page_table(dead);
 	if (copy_to_user((void __user *)arg, &p, sizeof(p))) {
 		drop_nodes(list, 1, p.addr, p.length); /* nothing leaks: the reference leaks the node here */
 		return -EFAULT;
@@ -265,6 +327,8 @@ static long ioctl_put_pages(struct file *filp, unsigned long arg)
 	 * on the same memory several times" (tests/amdp2ptest.c:296-299) */
 	p.released = (u32)drop_nodes(list, 1, p.addr, p.length);
 	p.reserved = 0;
+	MSG_INFO("PUT_PAGES: addr 0x%llx length 0x%llx -> %u pin(s) released\n", (unsigned long long)p.addr,
+		 (unsigned long long)p.length, p.released);
 	if (copy_to_user((void __user *)arg, &p, sizeof(p)))
 		return -EFAULT;
 	return 0;
@@ -342,6 +406,7 @@ static int b200p2ptest_mmap(struct file *filp, struct vm_area_struct *vma)
 	struct b200p2ptest_node *node;
 	int ret = -EINVAL;
 
+	MSG_INFO("mmap: GPU va 0x%llx size 0x%llx\n", (unsigned long long)gpu_va, (unsigned long long)size);
 	if (!size || (gpu_va & (PAGE_SIZE - 1)))
 		return -EINVAL;
 	mutex_lock(&list->lock);
@@ -401,6 +466,10 @@ static int __init b200p2ptest_init(void)
 		MSG_ERR("cannot register the misc device: %d\n", ret);
 		return ret;
 	}
+	/* load-time smoke check, as the reference prints its four KFD entry points (tests/amdp2ptest.c:441-445):
+	 * the addresses the NVIDIA P2P symbols resolved to -- a NULL here means nvidia.ko is not what we linked against */
+	MSG_INFO("nvidia_p2p_get_pages %p put_pages %p free_page_table %p dma_map_pages %p\n", (void *)nvidia_p2p_get_pages,
+		 (void *)nvidia_p2p_put_pages, (void *)nvidia_p2p_free_page_table, (void *)nvidia_p2p_dma_map_pages);
 	MSG_INFO("ready: %s, ABI %d, GPU page %llu KiB\n", B200P2PTEST_DEVICE_PATH, B200P2PTEST_ABI_VERSION,
 		 (unsigned long long)(B200P2P_GPU_PAGE_SIZE >> 10));
 	return 0;

@@ -87,16 +87,30 @@ int sim_mutex_lock(struct mutex *l);
 static inline void mutex_lock(struct mutex *l) { sim_mutex_lock(l); }
 static inline void mutex_unlock(struct mutex *l) { pthread_mutex_unlock(&l->m); }
 static inline void mutex_destroy(struct mutex *l) { pthread_mutex_destroy(&l->m); }
-typedef struct { volatile int counter; } atomic_t;
-static inline void atomic_set(atomic_t *a, int v) { a->counter = v; }
-static inline int atomic_read(const atomic_t *a) { return a->counter; }
-static inline int atomic_inc_return(atomic_t *a) { return __sync_add_and_fetch(&a->counter, 1); }
-static inline int atomic_dec_return(atomic_t *a) { return __sync_sub_and_fetch(&a->counter, 1); }
-static inline void atomic_inc(atomic_t *a) { __sync_add_and_fetch(&a->counter, 1); }
-static inline void atomic_dec(atomic_t *a) { __sync_sub_and_fetch(&a->counter, 1); }
-typedef struct { volatile long counter; } atomic64_t;
-static inline void atomic64_inc(atomic64_t *a) { __sync_add_and_fetch(&a->counter, 1); }
-static inline long atomic64_read(const atomic64_t *a) { return a->counter; }
+typedef struct { int counter; } atomic_t;
+static inline void atomic_set(atomic_t *a, int v) { __atomic_store_n(&a->counter, v, __ATOMIC_SEQ_CST); }
+static inline int atomic_read(const atomic_t *a) { return __atomic_load_n(&a->counter, __ATOMIC_SEQ_CST); }
+static inline int atomic_inc_return(atomic_t *a) { return __atomic_add_fetch(&a->counter, 1, __ATOMIC_SEQ_CST); }
+static inline int atomic_dec_return(atomic_t *a) { return __atomic_sub_fetch(&a->counter, 1, __ATOMIC_SEQ_CST); }
+static inline void atomic_inc(atomic_t *a) { __atomic_add_fetch(&a->counter, 1, __ATOMIC_SEQ_CST); }
+static inline void atomic_dec(atomic_t *a) { __atomic_sub_fetch(&a->counter, 1, __ATOMIC_SEQ_CST); }
+static inline int atomic_dec_and_test(atomic_t *a) { return __atomic_sub_fetch(&a->counter, 1, __ATOMIC_SEQ_CST) == 0; }
+typedef struct { long counter; } atomic64_t;
+static inline void atomic64_set(atomic64_t *a, long v) { __atomic_store_n(&a->counter, v, __ATOMIC_SEQ_CST); }
+static inline void atomic64_inc(atomic64_t *a) { __atomic_add_fetch(&a->counter, 1, __ATOMIC_SEQ_CST); }
+static inline void atomic64_dec(atomic64_t *a) { __atomic_sub_fetch(&a->counter, 1, __ATOMIC_SEQ_CST); }
+static inline long atomic64_read(const atomic64_t *a) { return __atomic_load_n(&a->counter, __ATOMIC_SEQ_CST); }
+
+/* ---- reference counting (linux/kref.h) */
+struct kref { atomic_t refcount; };
+static inline void kref_init(struct kref *k) { atomic_set(&k->refcount, 1); }
+static inline void kref_get(struct kref *k) { atomic_inc(&k->refcount); }
+static inline int kref_put(struct kref *k, void (*release)(struct kref *))
+{
+	if (atomic_dec_and_test(&k->refcount)) { release(k); return 1; }
+	return 0;
+}
+static inline unsigned int kref_read(const struct kref *k) { return (unsigned int)atomic_read(&k->refcount); }
 
 /* ---- lists */
 struct list_head { struct list_head *next, *prev; };
@@ -135,10 +149,25 @@ static inline void module_put(struct module *m) { atomic_dec(&m->refcnt); }
 #define MODULE_DESCRIPTION(x)
 #define MODULE_VERSION(x)
 #define MODULE_SOFTDEP(x)
-#define module_param(name, type, perm)
+/* A module parameter becomes a setter the tests can call: sim_param_<module>_<name>(value). */
+typedef unsigned int uint;
+typedef unsigned long ulong;
+#define module_param(name, type, perm) \
+	__attribute__((visibility("default"))) void SIM_CAT(SIM_CAT(SIM_CAT(sim_param_, KBUILD_MODNAME), _), name)(long v) { name = (type)v; }
 #define MODULE_PARM_DESC(name, desc)
 #define EXPORT_SYMBOL(x)
 size_t strscpy(char *dst, const char *src, size_t n);
+
+/* ---- debugfs + seq_file: one in-memory "file" per debugfs_create_file(); sim_debugfs_read() renders it */
+struct dentry { int unused; };
+struct seq_file { char *buf; size_t cap, len; void *private; };
+void seq_printf(struct seq_file *m, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
+struct sim_seq_ops { int (*show)(struct seq_file *, void *); };
+#define DEFINE_SHOW_ATTRIBUTE(name) static const struct sim_seq_ops name##_fops = { name##_show }
+struct dentry *debugfs_create_dir(const char *name, struct dentry *parent);
+struct dentry *debugfs_create_file(const char *name, unsigned short mode, struct dentry *parent, void *data, const struct sim_seq_ops *fops);
+void debugfs_remove_recursive(struct dentry *d);
+#define IS_ERR_OR_NULL(p) ((p) == NULL)
 
 /* ---- devices */
 struct device { int id; const char *name; };

@@ -36,7 +36,7 @@ void sim_log(int level, const char *fmt, ...)
 	va_list ap;
 
 	if (level >= 0 && level < 4)
-		g_log_count[level]++;
+		__atomic_add_fetch(&g_log_count[level], 1, __ATOMIC_RELAXED);
 	if (!g_verbose)
 		return;
 	va_start(ap, fmt);
@@ -50,11 +50,55 @@ int sim_mutex_lock(struct mutex *l)
 	int rc = pthread_mutex_lock(&l->m);
 
 	if (rc) { /* EDEADLK: the module tried to take a lock it already holds */
-		g_lock_errors++;
+		__atomic_add_fetch(&g_lock_errors, 1, __ATOMIC_RELAXED);
 		sim_log(0, "sim: mutex_lock error %d (recursive lock?)\n", rc);
 	}
 	return rc;
 }
+/* ------------------------------------------------------------------ debugfs / seq_file */
+#define MAX_DBGFS 8
+static struct { int live; char name[64]; const struct sim_seq_ops *fops; void *data; struct dentry d; } g_dbgfs[MAX_DBGFS];
+static struct dentry g_dbgfs_root;
+void seq_printf(struct seq_file *m, const char *fmt, ...)
+{
+	va_list ap;
+	int n;
+
+	va_start(ap, fmt);
+	n = vsnprintf(m->buf + m->len, m->cap > m->len ? m->cap - m->len : 0, fmt, ap);
+	va_end(ap);
+	if (n > 0) m->len += (size_t)n < m->cap - m->len ? (size_t)n : m->cap - m->len;
+}
+struct dentry *debugfs_create_dir(const char *name, struct dentry *parent) { return &g_dbgfs_root; }
+struct dentry *debugfs_create_file(const char *name, unsigned short mode, struct dentry *parent, void *data, const struct sim_seq_ops *fops)
+{
+	int i;
+
+	for (i = 0; i < MAX_DBGFS; i++)
+		if (!g_dbgfs[i].live) {
+			g_dbgfs[i].live = 1; g_dbgfs[i].fops = fops; g_dbgfs[i].data = data;
+			snprintf(g_dbgfs[i].name, sizeof g_dbgfs[i].name, "%s", name);
+			return &g_dbgfs[i].d;
+		}
+	return NULL;
+}
+void debugfs_remove_recursive(struct dentry *d) { int i; if (d) for (i = 0; i < MAX_DBGFS; i++) g_dbgfs[i].live = 0; }
+/* cat <debugfs>/.../<name>: returns the length, or -ENOENT */
+SIM_API int sim_debugfs_read(const char *name, char *out, int cap)
+{
+	struct seq_file m = { out, (size_t)cap, 0, NULL };
+	int i;
+
+	for (i = 0; i < MAX_DBGFS; i++)
+		if (g_dbgfs[i].live && !strcmp(g_dbgfs[i].name, name)) {
+			m.private = g_dbgfs[i].data;
+			if (cap > 0) out[0] = 0;
+			g_dbgfs[i].fops->show(&m, NULL);
+			return (int)m.len;
+		}
+	return -ENOENT;
+}
+
 size_t strscpy(char *dst, const char *src, size_t n)
 {
 	size_t l = strlen(src);
@@ -94,7 +138,7 @@ SIM_API int sim_module_refcount(void) { return atomic_read(&sim_this_module.refc
 #define MAX_PINS 256
 struct gpu_alloc { u64 va, size; int live; };
 struct pin {
-	int live, revoked;
+	int live, revoked, cb_done;
 	u64 va, size;
 	struct nvidia_p2p_page_table *pt;
 	void (*cb)(void *);
@@ -105,15 +149,23 @@ static struct pin g_pins[MAX_PINS];
 static pthread_mutex_t g_nv_lock = PTHREAD_MUTEX_INITIALIZER;
 static int g_live_pt, g_live_map, g_misuse, g_fail_next_get_pages, g_fail_next_dma_map;
 static int g_revoke_during_get_pages; /* fire the free callback from inside get_pages (early revoke) */
+static void (*g_dma_map_hook)(void);
+static int g_concurrent;   /* multi-threaded stress: unpin / unmap calls may legitimately cross a revoke they could not have seen */
 
 SIM_API int sim_gpu_alloc(u64 va, u64 size)
 {
 	int i;
 
+	int rc = -ENOMEM;
+
 	if ((va | size) & (GPU_PAGE - 1) || !size) return -EINVAL;
+	pthread_mutex_lock(&g_nv_lock);
 	for (i = 0; i < MAX_ALLOCS; i++)
-		if (!g_allocs[i].live) { g_allocs[i].va = va; g_allocs[i].size = size; g_allocs[i].live = 1; return 0; }
-	return -ENOMEM;
+		if (g_allocs[i].live && g_allocs[i].va == va && g_allocs[i].size == size) { rc = 0; break; }   /* already known */
+	for (i = 0; rc && i < MAX_ALLOCS; i++)
+		if (!g_allocs[i].live) { g_allocs[i].va = va; g_allocs[i].size = size; g_allocs[i].live = 1; rc = 0; }
+	pthread_mutex_unlock(&g_nv_lock);
+	return rc;
 }
 static int range_is_gpu(u64 va, u64 size)
 {
@@ -124,6 +176,17 @@ static int range_is_gpu(u64 va, u64 size)
 	return 0;
 }
 SIM_API u64 sim_gpu_bus_addr(u64 va) { return va ^ BUS_XOR; }
+/* With several threads a put_pages / dma_unmap_pages can be decided before, and arrive after, a revoke: the driver
+ * refuses it and that is not a client bug.  The ordering rules are enforced by the single-threaded scenarios; the
+ * stress keeps the checks that hold under any interleaving (unknown or double-freed page table, a freed page table
+ * handed to the driver, leaks). */
+SIM_API void sim_nv_set_concurrent(int on) { g_concurrent = on; }
+/* Revoke allocation `va` from INSIDE the client's next nvidia_p2p_dma_map_pages() call (one shot): the window in which
+ * the client has dropped its lock and handed the page table to the driver. */
+static u64 g_hook_free_va;
+SIM_API int sim_gpu_free(u64 va);
+static void hook_free_once(void) { u64 va = g_hook_free_va; g_dma_map_hook = NULL; g_hook_free_va = 0; if (va) sim_gpu_free(va); }
+SIM_API void sim_nv_revoke_during_dma_map(u64 va) { g_hook_free_va = va; g_dma_map_hook = va ? hook_free_once : NULL; }
 SIM_API int sim_live_page_tables(void) { return g_live_pt; }
 SIM_API int sim_live_dma_mappings(void) { return g_live_map; }
 SIM_API int sim_nv_misuse(void) { return g_misuse; }
@@ -153,7 +216,7 @@ int nvidia_p2p_get_pages(uint64_t token, uint32_t va_space, uint64_t va, uint64_
 		pt->pages[i] = calloc(1, sizeof(struct nvidia_p2p_page));
 		pt->pages[i]->physical_address = sim_gpu_bus_addr(va + (u64)i * GPU_PAGE);
 	}
-	g_pins[slot] = (struct pin){ 1, 0, va, len, pt, free_callback, data };
+	g_pins[slot] = (struct pin){ 1, 0, 0, va, len, pt, free_callback, data };
 	g_live_pt++;
 	*page_table = pt;
 	pthread_mutex_unlock(&g_nv_lock);
@@ -164,6 +227,9 @@ int nvidia_p2p_get_pages(uint64_t token, uint32_t va_space, uint64_t va, uint64_
 		g_pins[slot].revoked = 1;
 		pthread_mutex_unlock(&g_nv_lock);
 		free_callback(data);
+		pthread_mutex_lock(&g_nv_lock);
+		if (g_pins[slot].live && g_pins[slot].pt == pt) g_pins[slot].cb_done = 1;
+		pthread_mutex_unlock(&g_nv_lock);
 	}
 	return 0;
 }
@@ -190,7 +256,14 @@ int nvidia_p2p_put_pages(uint64_t token, uint32_t va_space, uint64_t va, struct 
 	pthread_mutex_lock(&g_nv_lock);
 	p = find_pin(pt);
 	if (!p) { g_misuse++; pthread_mutex_unlock(&g_nv_lock); sim_log(0, "nv-p2p: put_pages on an unknown page table\n"); return -EINVAL; }
-	if (p->revoked) { g_misuse++; pthread_mutex_unlock(&g_nv_lock); sim_log(0, "nv-p2p: put_pages after the free callback\n"); return -EINVAL; }
+	if (p->revoked) {
+		/* Once the free callback has RETURNED the client knows the pin is gone: unpinning it is a bug.  While the
+		 * revoke is still in flight the client could not know -- the driver just refuses, and the page table
+		 * stays the client's to release with nvidia_p2p_free_page_table(). */
+		if (p->cb_done && !g_concurrent) { g_misuse++; sim_log(0, "nv-p2p: put_pages after the free callback\n"); }
+		pthread_mutex_unlock(&g_nv_lock);
+		return -EINVAL;
+	}
 	if (p->va != va) { g_misuse++; pthread_mutex_unlock(&g_nv_lock); return -EINVAL; }
 	p->live = 0;
 	destroy_pt(pt);
@@ -218,6 +291,14 @@ int nvidia_p2p_dma_map_pages(struct pci_dev *peer, struct nvidia_p2p_page_table 
 
 	if (!peer || !pt || !out) return -EINVAL;
 	if (g_fail_next_dma_map > 0 && --g_fail_next_dma_map == 0) return -EIO;
+	if (g_dma_map_hook) g_dma_map_hook();                 /* tests: something happens while the client is inside the driver */
+	pthread_mutex_lock(&g_nv_lock);
+	if (!find_pin(pt)) {                                    /* a freed page table reached the driver: the bug pt_users prevents */
+		g_misuse++;
+		pthread_mutex_unlock(&g_nv_lock);
+		sim_log(0, "nv-p2p: dma_map_pages on a page table that no longer exists\n");
+		return -EINVAL;
+	}
 	m = calloc(1, sizeof(*m));
 	m->version = 0x00020003; m->page_size_type = NVIDIA_P2P_PAGE_SIZE_64KB; m->entries = pt->entries;
 	m->dma_addresses = calloc(pt->entries, sizeof(u64));
@@ -226,6 +307,7 @@ int nvidia_p2p_dma_map_pages(struct pci_dev *peer, struct nvidia_p2p_page_table 
 	m->pci_dev = peer;
 	g_live_map++;
 	*out = m;
+	pthread_mutex_unlock(&g_nv_lock);
 	return 0;
 }
 static void destroy_map(struct nvidia_p2p_dma_mapping *m) { free(m->dma_addresses); free(m); g_live_map--; }
@@ -236,7 +318,8 @@ int nvidia_p2p_dma_unmap_pages(struct pci_dev *peer, struct nvidia_p2p_page_tabl
 	if (!m) return -EINVAL;
 	pthread_mutex_lock(&g_nv_lock);
 	p = pt ? find_pin(pt) : NULL;
-	if (p && p->revoked) { g_misuse++; sim_log(0, "nv-p2p: dma_unmap_pages after the free callback\n"); }
+	if (p && p->revoked && p->cb_done && !g_concurrent) { g_misuse++; sim_log(0, "nv-p2p: dma_unmap_pages after the free callback\n"); }
+	if (pt && !p) { g_misuse++; sim_log(0, "nv-p2p: dma_unmap_pages with a page table that no longer exists\n"); }
 	if (peer != m->pci_dev) { g_misuse++; sim_log(0, "nv-p2p: dma_unmap_pages for a different device\n"); }
 	destroy_map(m);
 	pthread_mutex_unlock(&g_nv_lock);
@@ -254,7 +337,7 @@ int nvidia_p2p_free_dma_mapping(struct nvidia_p2p_dma_mapping *m)
 /* cudaFree / process exit: every live pin overlapping the allocation is revoked (callbacks run unlocked). */
 SIM_API int sim_gpu_free(u64 va)
 {
-	struct { void (*cb)(void *); void *data; } fire[MAX_PINS];
+	struct { void (*cb)(void *); void *data; int slot; struct nvidia_p2p_page_table *pt; } fire[MAX_PINS];
 	int i, a = -1, n = 0;
 
 	pthread_mutex_lock(&g_nv_lock);
@@ -266,19 +349,38 @@ SIM_API int sim_gpu_free(u64 va)
 		if (!p->live || p->revoked) continue;
 		if (p->va + p->size <= g_allocs[a].va || p->va >= g_allocs[a].va + g_allocs[a].size) continue;
 		p->revoked = 1;
-		if (p->cb) { fire[n].cb = p->cb; fire[n].data = p->cb_data; n++; }
+		if (p->cb) { fire[n].cb = p->cb; fire[n].data = p->cb_data; fire[n].slot = i; fire[n].pt = p->pt; n++; }
 		else { /* a pin without a callback simply disappears with the memory */ p->live = 0; destroy_pt(p->pt); }
 	}
 	g_allocs[a].live = 0;
 	pthread_mutex_unlock(&g_nv_lock);
-	for (i = 0; i < n; i++) fire[i].cb(fire[i].data);
+	for (i = 0; i < n; i++) {
+		fire[i].cb(fire[i].data);
+		pthread_mutex_lock(&g_nv_lock);
+		if (g_pins[fire[i].slot].live && g_pins[fire[i].slot].pt == fire[i].pt) g_pins[fire[i].slot].cb_done = 1;
+		pthread_mutex_unlock(&g_nv_lock);
+	}
 	return n;
 }
 
 /* ------------------------------------------------------------------ mock ib_core (PeerDirect core) */
-#define MAX_MRS 64
+/*
+ * Thread model (what the real PeerDirect core guarantees, so that what is left to the CLIENT is exercised):
+ *   * teardown of an MR (dma_unmap + put_pages) happens exactly once, under the MR's lock -- whoever gets there
+ *     first, the invalidate upcall (synchronous mode) or dereg;
+ *   * release is called once, after the teardown, by dereg -- or, with sim_ib_set_release_in_invalidate(1), from
+ *     INSIDE the invalidate upcall (an ib_core that destroys the MR on invalidation), in which case the client's
+ *     free callback returns into a context that ib_core has already released;
+ *   * nothing orders a dereg on one thread against the client's free callback on another beyond that lock: the
+ *     callback's epilogue (after the upcall) may run concurrently with release.
+ */
+#define MAX_MRS 256
 struct sim_mr {
-	int live, invalidated, torn_down;
+	int live, invalidated, torn_down, released;
+	int registering;         /* reg_mr still running: the MR is not published yet, an invalidation may tear the pin down but
+	                          * never destroys (releases) it -- the registering thread does, when it gets back */
+	u32 gen;                 /* bumped on every (re)use of the slot: core_context = ticket (gen << 16 | slot), never reused */
+	pthread_mutex_t lock;
 	void *client_ctx;
 	struct sg_table sg;
 	int nmap;
@@ -287,16 +389,19 @@ struct sim_mr {
 };
 static const struct peer_memory_client *g_client;
 static struct sim_mr g_mrs[MAX_MRS];
-static int g_refuse_registration, g_sync_invalidate = 1, g_invalidate_calls;
+static pthread_mutex_t g_ib_lock = PTHREAD_MUTEX_INITIALIZER;   /* slot allocation */
+static int g_refuse_registration, g_sync_invalidate = 1, g_invalidate_calls, g_release_in_invalidate;
 static int g_reg_handle_token;
 
 SIM_API void sim_ib_set_refuse(int on) { g_refuse_registration = on; }
 SIM_API void sim_ib_set_sync_invalidate(int on) { g_sync_invalidate = on; }
-SIM_API int sim_ib_invalidate_calls(void) { return g_invalidate_calls; }
+SIM_API void sim_ib_set_release_in_invalidate(int on) { g_release_in_invalidate = on; }
+SIM_API int sim_ib_invalidate_calls(void) { return __atomic_load_n(&g_invalidate_calls, __ATOMIC_SEQ_CST); }
 SIM_API const char *sim_ib_client_name(void) { return g_client ? g_client->name : ""; }
 SIM_API const char *sim_ib_client_version(void) { return g_client ? g_client->version : ""; }
 
-static void mr_teardown(struct sim_mr *mr)
+/* caller holds mr->lock */
+static void mr_teardown_locked(struct sim_mr *mr)
 {
 	if (mr->torn_down) return;
 	mr->torn_down = 1;
@@ -305,12 +410,21 @@ static void mr_teardown(struct sim_mr *mr)
 }
 static int sim_invalidate(void *reg_handle, u64 core_context)
 {
-	struct sim_mr *mr = (struct sim_mr *)(uintptr_t)core_context;
+	/* core_context is a ticket, as in the real PeerDirect core: a late invalidation of an MR that is already gone
+	 * (its slot possibly re-used by another registration) must find nothing */
+	const u32 slot = (u32)(core_context & 0xffff), gen = (u32)(core_context >> 16);
+	struct sim_mr *mr = slot < MAX_MRS ? &g_mrs[slot] : NULL;
+	void *ctx = NULL;
 
-	g_invalidate_calls++;
-	if (reg_handle != &g_reg_handle_token || !mr || !mr->live) return -EINVAL;
+	__atomic_add_fetch(&g_invalidate_calls, 1, __ATOMIC_SEQ_CST);
+	if (reg_handle != &g_reg_handle_token || !mr) return -EINVAL;
+	pthread_mutex_lock(&mr->lock);
+	if (!mr->live || mr->gen != gen) { pthread_mutex_unlock(&mr->lock); return -EINVAL; }
 	mr->invalidated = 1;
-	if (g_sync_invalidate) mr_teardown(mr); /* re-enters the client from inside its free callback */
+	if (g_sync_invalidate) mr_teardown_locked(mr); /* re-enters the client from inside its free callback */
+	if (g_sync_invalidate && g_release_in_invalidate && !mr->released && !mr->registering) { mr->released = 1; ctx = mr->client_ctx; }
+	pthread_mutex_unlock(&mr->lock);
+	if (ctx) g_client->release(ctx);               /* the MR is destroyed from inside the upcall */
 	return 0;
 }
 void *ib_register_peer_memory_client(const struct peer_memory_client *c, invalidate_peer_memory *cb)
@@ -328,41 +442,102 @@ void ib_unregister_peer_memory_client(void *h) { if (h == &g_reg_handle_token) g
 SIM_API long sim_ib_reg_mr(u64 addr, u64 size, int dev_id)
 {
 	struct sim_mr *mr = NULL;
+	void *ctx = NULL;
 	int i, rc;
 
 	if (!g_client) return -ENODEV;
-	for (i = 0; i < MAX_MRS; i++) if (!g_mrs[i].live) { mr = &g_mrs[i]; break; }
-	if (!mr) return -ENOMEM;
-	memset(mr, 0, sizeof(*mr));
+	if (!g_client->acquire((unsigned long)addr, (size_t)size, NULL, NULL, &ctx)) return -EOPNOTSUPP; /* not ours */
+	pthread_mutex_lock(&g_ib_lock);
+	for (i = 0; i < MAX_MRS; i++) {
+		int free_slot;
+
+		pthread_mutex_lock(&g_mrs[i].lock); free_slot = !g_mrs[i].live; pthread_mutex_unlock(&g_mrs[i].lock);
+		if (free_slot) { mr = &g_mrs[i]; break; }
+	}
+	if (mr) {
+		/* fields are re-initialised under the slot's own lock: a late invalidation may be looking at it */
+		pthread_mutex_lock(&mr->lock);
+		mr->gen++;
+		mr->invalidated = mr->torn_down = mr->released = 0;
+		mr->client_ctx = NULL; mr->nmap = 0; memset(&mr->sg, 0, sizeof mr->sg);
+		mr->live = 1; mr->registering = 1;
+		pthread_mutex_unlock(&mr->lock);
+	}
+	pthread_mutex_unlock(&g_ib_lock);
+	if (!mr) { g_client->release(ctx); return -ENOMEM; }
+	pthread_mutex_lock(&mr->lock);
+	mr->client_ctx = ctx;
 	mr->pdev.dev.id = dev_id; mr->pdev.vendor = 0x15b3;
-	if (!g_client->acquire((unsigned long)addr, (size_t)size, NULL, NULL, &mr->client_ctx)) return -EOPNOTSUPP; /* not ours */
-	mr->live = 1;
 	mr->page_size = g_client->get_page_size(mr->client_ctx);
-	rc = g_client->get_pages((unsigned long)addr, (size_t)size, 1, 1, &mr->sg, mr->client_ctx, (u64)(uintptr_t)mr);
-	if (rc) { g_client->release(mr->client_ctx); mr->live = 0; return rc; }
-	rc = g_client->dma_map(&mr->sg, mr->client_ctx, &mr->pdev.dev, 0, &mr->nmap);
-	if (rc) { g_client->put_pages(&mr->sg, mr->client_ctx); g_client->release(mr->client_ctx); mr->live = 0; return rc; }
+	pthread_mutex_unlock(&mr->lock);
+	/* get_pages / dma_map run WITHOUT the MR lock: a revoke may fire (and call sim_invalidate) while they do */
+	rc = g_client->get_pages((unsigned long)addr, (size_t)size, 1, 1, &mr->sg, ctx, ((u64)mr->gen << 16) | (u64)i);
+	if (!rc) {
+		int pinned_only = 0;
+
+		rc = g_client->dma_map(&mr->sg, ctx, &mr->pdev.dev, 0, &mr->nmap);
+		pthread_mutex_lock(&mr->lock);
+		/* an invalidation that ran meanwhile may have torn the MR down, or even released the context: neither may be
+		 * repeated here */
+		if (rc && !mr->torn_down && !mr->released) { mr->torn_down = 1; pinned_only = 1; }
+		pthread_mutex_unlock(&mr->lock);
+		if (pinned_only) g_client->put_pages(&mr->sg, ctx);
+	}
+	{
+		int rel, gone;
+
+		pthread_mutex_lock(&mr->lock);
+		mr->registering = 0;
+		/* an invalidation arrived while the MR was being registered and this ib_core destroys MRs on invalidation:
+		 * it could not do so under our feet, so it falls to us now */
+		if (!rc && mr->invalidated && g_release_in_invalidate && !mr->released) { mr_teardown_locked(mr); rc = -EFAULT; }
+		gone = mr->released;
+		rel = rc && !mr->released;
+		if (rel) { mr->released = 1; mr->torn_down = 1; }
+		pthread_mutex_unlock(&mr->lock);
+		if (rel) g_client->release(ctx);
+		if (rc || gone) {
+			pthread_mutex_lock(&mr->lock); mr->live = 0; pthread_mutex_unlock(&mr->lock);
+			return rc ? rc : -EFAULT;
+		}
+	}
 	return i;
 }
 SIM_API int sim_ib_mr_nmap(long id) { return g_mrs[id].nmap; }
 SIM_API u64 sim_ib_mr_page_size(long id) { return g_mrs[id].page_size; }
-SIM_API int sim_ib_mr_invalidated(long id) { return g_mrs[id].invalidated; }
+SIM_API int sim_ib_mr_invalidated(long id)
+{
+	int v;
+
+	pthread_mutex_lock(&g_mrs[id].lock); v = g_mrs[id].invalidated; pthread_mutex_unlock(&g_mrs[id].lock);
+	return v;
+}
 SIM_API int sim_ib_mr_dma(long id, int i, u64 *addr, u64 *len)
 {
 	struct sim_mr *mr = &g_mrs[id];
+	int rc = -EINVAL;
 
-	if (!mr->live || mr->torn_down || i < 0 || i >= (int)mr->sg.nents) return -EINVAL;
-	*addr = mr->sg.sgl[i].dma_address; *len = mr->sg.sgl[i].dma_length;
-	return 0;
+	pthread_mutex_lock(&mr->lock);
+	if (mr->live && !mr->torn_down && i >= 0 && i < (int)mr->sg.nents) {
+		*addr = mr->sg.sgl[i].dma_address; *len = mr->sg.sgl[i].dma_length;
+		rc = 0;
+	}
+	pthread_mutex_unlock(&mr->lock);
+	return rc;
 }
 SIM_API int sim_ib_dereg_mr(long id)
 {
 	struct sim_mr *mr = &g_mrs[id];
+	void *ctx = NULL;
 
-	if (id < 0 || id >= MAX_MRS || !mr->live) return -EINVAL;
-	mr_teardown(mr);
-	g_client->release(mr->client_ctx);
-	mr->live = 0;
+	if (id < 0 || id >= MAX_MRS) return -EINVAL;
+	pthread_mutex_lock(&mr->lock);
+	if (!mr->live) { pthread_mutex_unlock(&mr->lock); return -EINVAL; }
+	mr_teardown_locked(mr);
+	if (!mr->released) { mr->released = 1; ctx = mr->client_ctx; }
+	pthread_mutex_unlock(&mr->lock);
+	if (ctx) g_client->release(ctx);
+	pthread_mutex_lock(&mr->lock); mr->live = 0; pthread_mutex_unlock(&mr->lock);
 	return 0;
 }
 /* Out-of-order / malformed sequences the real ib_core never produces but the client must survive. */
@@ -472,7 +647,19 @@ SIM_API void sim_reset(void)
 {
 	memset(g_allocs, 0, sizeof g_allocs);
 	memset(g_pins, 0, sizeof g_pins);
-	memset(g_mrs, 0, sizeof g_mrs);
+	{
+		static int locks_ready;
+		int k;
+
+		for (k = 0; k < MAX_MRS; k++) {
+			pthread_mutex_t keep = g_mrs[k].lock;
+			memset(&g_mrs[k], 0, sizeof g_mrs[k]);
+			if (locks_ready) g_mrs[k].lock = keep; else pthread_mutex_init(&g_mrs[k].lock, NULL);
+		}
+		locks_ready = 1;
+	}
+	memset(g_dbgfs, 0, sizeof g_dbgfs);
+	g_release_in_invalidate = 0; g_dma_map_hook = NULL; g_concurrent = 0;
 	g_live_pt = g_live_map = g_misuse = 0;
 	g_fail_next_get_pages = g_fail_next_dma_map = g_revoke_during_get_pages = 0;
 	g_refuse_registration = 0; g_sync_invalidate = 1; g_invalidate_calls = 0;

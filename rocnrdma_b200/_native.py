@@ -148,6 +148,9 @@ _SIGS = {
     "rn_k_compare": (i32, [u64, u64, u64, u64, u64]),
     "rn_k_l2_flush": (i32, [u64, u64, u64, u32]),
     # ---- ConnectX backend (csrc/verbs/verbs_dl.cc): libibverbs / mlx5dv through dlopen
+    "rn_buffer_id": (i32, [u64, C.POINTER(u64)]),
+    "rn_hca_sweep_revoked": (i32, [vp]),
+    "rn_mr_driver_revoked": (i32, [vp, u32]),
     "rn_qp_adopt": (i32, [vp, C.POINTER(RnGpuQp), C.POINTER(vp)]),
     "rn_qp_is_adopted": (i32, [vp]),
     "rn_verbs_compiled": (i32, []),

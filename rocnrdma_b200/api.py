@@ -104,6 +104,11 @@ class MemoryRegion:
             return "PINNED" if self._live else "FREE"
         return ["FREE", "PINNED", "REVOKED"][self.ctx._lib.rn_mr_state(self.ctx._h, self.key)]
 
+    @property
+    def driver_revoked(self) -> bool:
+        """True when the revocation came from the driver's side (the allocation vanished), not from ``revoke()``."""
+        return self.ctx.wire == "softhca" and bool(self.ctx._lib.rn_mr_driver_revoked(self.ctx._h, self.key))
+
     def revoke(self):
         """The backing memory is going away: stop translating now (the engine fails
         any WQE that names this key with a protection error)."""
@@ -225,6 +230,7 @@ class QueuePair:
     def _post(self, opcode, laddr, lkey, raddr, rkey, nbytes, signaled=True, imm=0) -> int:
         idx = C.c_uint64()
         flags = W.CTRL_CQ_UPDATE if signaled else 0
+        self.ctx.sweep_revoked()          # a freed allocation must not be reachable through a stale key
         N.check(self.ctx._lib.rn_post_send(self._q, opcode, laddr, lkey, raddr, rkey, nbytes, flags, imm,
                                            C.byref(idx)), "post_send")
         return idx.value
@@ -587,6 +593,41 @@ class Context:
             errs.append(f"{how}: {self._lib.rn_verbs_why().decode(errors='replace')}")
         raise N.NativeError("reg_mr failed: " + "; ".join(errs))
 
+    def sweep_revoked(self) -> int:
+        """Driver-originated revocation: ask the CUDA driver whether the allocation behind every device-memory
+        registration still exists (allocation id recorded at ``reg_mr``); registrations whose memory was freed --
+        ``cudaFree``, ``torch.cuda.empty_cache()`` of the segment, or the address re-used by a new allocation -- are
+        revoked (their MKey stops translating: a WQE that names it completes with a protection error instead of
+        touching the address).  Returns how many were revoked now.  ``reg_mr(tensor)`` keeps a reference to the tensor,
+        so this only ever fires for raw ``(ptr, nbytes)`` registrations or storage resized under the MR.
+        The kernel-side counterpart is the free callback of ``kmod/b200p2p.c`` (reference: amdp2p.c:88-109)."""
+        if self.wire != "softhca" or not self._h:
+            return 0
+        n = self._lib.rn_hca_sweep_revoked(self._h)
+        if n < 0:
+            raise N.NativeError(f"sweep_revoked failed ({n})")
+        return n
+
+    def watch_revocations(self, period_s: float = 0.05):
+        """Start a daemon thread that calls :meth:`sweep_revoked` every ``period_s`` (the stand-in for an asynchronous
+        free callback when nobody on the host touches the context between a free and the next GPU-posted WQE)."""
+        import threading
+        if getattr(self, "_watch", None):
+            return
+        stop = threading.Event()
+
+        def run():
+            while not stop.wait(period_s):
+                if self._closed:
+                    return
+                try:
+                    self.sweep_revoked()
+                except Exception:
+                    return
+        t = threading.Thread(target=run, daemon=True)
+        self._watch = (t, stop)
+        t.start()
+
     def enable_peer(self, peer_device: int):
         """Allow this context's GPU to reach ``peer_device``'s memory over NVLink (needed before
         connecting a QP to a QP of a context that lives on that GPU)."""
@@ -694,6 +735,8 @@ class Context:
         """Stop the engine and free the HCA (queues, CQs, control arenas).  Registered tensors are untouched."""
         if not self._closed:
             self._closed = True
+            if getattr(self, "_watch", None):
+                self._watch[1].set()
             if self._vdev:
                 for q in self._vqps:
                     q.destroy()

@@ -787,8 +787,11 @@ __global__ void __launch_bounds__(kThreads, 1) engine_kernel(EngineCtl* ctl) {
       // a batch claim is parsed by the whole first warp; its chunks are then drawn like anybody else's
       batch_k = __shfl_sync(0xffffffffu, batch_k, 0);
       if (batch_k) {
-        QpDev* bqp = (QpDev*)__shfl_sync(0xffffffffu, (unsigned long long)work.qp, 0);
-        unsigned long long bw = __shfl_sync(0xffffffffu, work.w, 0);
+        // only lane 0 reads the (shared-memory) work record it wrote; the other lanes' operand is ignored by the shuffle
+        unsigned long long wq0 = 0, ww0 = 0;
+        if (threadIdx.x == 0) { wq0 = (unsigned long long)*(QpDev* volatile*)&work.qp; ww0 = *(volatile unsigned long long*)&work.w; }
+        QpDev* bqp = (QpDev*)__shfl_sync(0xffffffffu, wq0, 0);
+        unsigned long long bw = __shfl_sync(0xffffffffu, ww0, 0);
         claim_batch(ctl, bqp, bw, (uint32_t)batch_k, threadIdx.x);
       }
     }
@@ -852,8 +855,11 @@ __global__ void __launch_bounds__(kThreads, 1) engine_kernel(EngineCtl* ctl) {
       }
     }
     if (threadIdx.x < 32) {
-      if (__shfl_sync(0xffffffffu, finished, 0))
-        retire((QpDev*)__shfl_sync(0xffffffffu, (unsigned long long)work.qp, 0), threadIdx.x, work.w);
+      if (__shfl_sync(0xffffffffu, finished, 0)) {
+        unsigned long long wq0 = 0, ww0 = 0;
+        if (threadIdx.x == 0) { wq0 = (unsigned long long)*(QpDev* volatile*)&work.qp; ww0 = *(volatile unsigned long long*)&work.w; }
+        retire((QpDev*)__shfl_sync(0xffffffffu, wq0, 0), threadIdx.x, ww0);
+      }
     }
   }
   if (threadIdx.x == 0) {

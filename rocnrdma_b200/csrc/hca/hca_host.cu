@@ -49,6 +49,8 @@ struct Mr {
   bool host_registered_by_us = false;
   int dmabuf_fd = -1;
   uint8_t tag = 0;
+  uint64_t buffer_id = 0;     // CUDA allocation identity at registration (device memory); 0 = not tracked
+  bool driver_revoked = false;
 };
 
 struct Cq {
@@ -289,6 +291,7 @@ RN_API int rn_classify_ptr(uint64_t ptr, int* device_out) {
   return 0;
 }
 
+extern "C" int rn_buffer_id(uint64_t ptr, uint64_t* id) __attribute__((weak));
 extern "C" int rn_dmabuf_export(uint64_t ptr, uint64_t len, int* cu_err_out) __attribute__((weak));
 extern "C" int rn_dmabuf_close(int fd) __attribute__((weak));
 
@@ -356,6 +359,7 @@ RN_API int rn_reg_mr(void* hca, uint64_t ptr, uint64_t len, uint32_t access, uin
   for (; idx < h->max_mkeys; ++idx)
     if (h->mrs[idx].state == MR_FREE) break;
   if (idx == h->max_mkeys) return fail(-12, "reg_mr: MKey table full (%u)", h->max_mkeys);
+  if (cls == 1 && rn_buffer_id) rn_buffer_id(ptr, &m.buffer_id);
   m.tag = (uint8_t)(h->mrs[idx].tag + 1);  // a recycled index never yields the old key
   m.state = MR_PINNED;
   m.base = ptr; m.len = len; m.access = access;
@@ -391,6 +395,40 @@ RN_API int rn_mr_revoke(void* hca, uint32_t key) {
   h->mrs[i].state = MR_REVOKED;
   if (h->mrs[i].dmabuf_fd >= 0 && rn_dmabuf_close) { rn_dmabuf_close(h->mrs[i].dmabuf_fd); h->mrs[i].dmabuf_fd = -1; }   // the pin goes with the memory
   return 0;
+}
+
+// Driver-originated revocation.  The kernel bridge learns that pinned memory is going away through the GPU
+// driver's free callback (kmod/b200p2p.c: b200_free_callback; reference amdp2p.c:88-109).  A userspace HCA has no
+// such upcall, so it asks the driver: every device-memory registration remembers the CUDA allocation id it was
+// made on; a registration whose pointer the driver no longer knows, or that now belongs to a different
+// allocation, is revoked exactly as if the callback had fired (MKey stops translating, the dma-buf pin is
+// dropped).  Called by the host-side post path and the kernel launch wrappers, by Context.sweep_revoked(), and by
+// the optional watcher thread.  Returns the number of registrations revoked by this call.
+RN_API int rn_hca_sweep_revoked(void* hca) {
+  Hca* h = (Hca*)hca;
+  if (!rn_buffer_id) return 0;
+  std::lock_guard<std::mutex> g(h->mu);
+  cudaSetDevice(h->dev);
+  int n = 0;
+  for (uint32_t i = 0; i < h->max_mkeys; ++i) {
+    Mr& m = h->mrs[i];
+    if (m.state != MR_PINNED || !m.buffer_id) continue;
+    uint64_t now = 0;
+    const int rc = rn_buffer_id(m.base, &now);
+    if (rc == 0 && now == m.buffer_id) continue;
+    uint32_t zero = 0;
+    if (push(h, &h->d_mkeys[i].valid, &zero, sizeof zero)) continue;
+    m.state = MR_REVOKED;
+    m.driver_revoked = true;
+    if (m.dmabuf_fd >= 0 && rn_dmabuf_close) { rn_dmabuf_close(m.dmabuf_fd); m.dmabuf_fd = -1; }
+    ++n;
+  }
+  return n;
+}
+RN_API int rn_mr_driver_revoked(void* hca, uint32_t key) {
+  Hca* h = (Hca*)hca;
+  uint32_t i = key >> 8;
+  return i < h->max_mkeys && h->mrs[i].key == key && h->mrs[i].driver_revoked ? 1 : 0;
 }
 
 RN_API int rn_dereg_mr(void* hca, uint32_t key) {

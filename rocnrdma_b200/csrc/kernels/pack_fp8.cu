@@ -230,7 +230,9 @@ __global__ void __launch_bounds__(kPackThreads) unpack_fp8_kernel(UnpackArgs a) 
         fence_gpu();
       }
       __syncthreads();
-      if (!ok) break;
+      const int good = ok;
+      __syncthreads();          // everybody has read `ok` before thread 0 re-arms it for the next record
+      if (!good) break;
     }
     const uint8_t* recp = a.staging + (uint64_t)chunk * rec;
     for (uint32_t t = blockIdx.x; t < tiles_per_chunk; t += gridDim.x) {

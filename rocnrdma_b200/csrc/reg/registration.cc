@@ -85,3 +85,17 @@ RN_API int rn_device_caps(int dev) {
 RN_API int rn_device_pci(int dev, char* out, int n) {
   return cudaDeviceGetPCIBusId(out, n, dev) == cudaSuccess ? 0 : -19;
 }
+
+// Identity of the allocation behind a device pointer (CU_POINTER_ATTRIBUTE_BUFFER_ID): unique per allocation for
+// the life of the process, so "the memory under this registration was freed" -- and even "freed and the address
+// handed out again" -- is observable from userspace.  Returns 0 and *id, or -22 when the driver no longer knows
+// the pointer (it was freed).  This is the userspace stand-in for the kernel-side free callback
+// (nvidia_p2p_get_pages' free_callback; the reference's free_callback, amdp2p.c:88-109).
+RN_API int rn_buffer_id(uint64_t ptr, uint64_t* id) {
+  static PointerGetAttributeFn fn = entry<PointerGetAttributeFn>("cuPointerGetAttribute");
+  if (!fn) return -38;
+  unsigned long long v = 0;
+  if (fn(&v, CU_POINTER_ATTRIBUTE_BUFFER_ID, (CUdeviceptr)ptr) != CUDA_SUCCESS) return -22;
+  *id = (uint64_t)v;
+  return 0;
+}

@@ -22,6 +22,8 @@ def work_stream(ctx, stream=None):
     # native launchers use the calling thread's current device: make it this context's (creating a
     # second Context, or torch work on another GPU, may have changed it)
     N.load().rn_set_device(ctx.device)
+    if getattr(ctx, "auto_sweep", True):
+        ctx.sweep_revoked()               # driver-originated revocation check before a kernel may post (one driver query per MR)
     if stream is not None and int(stream.cuda_stream) != 0:
         return stream
     cur = torch.cuda.current_stream(ctx.device)

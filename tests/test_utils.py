@@ -9,9 +9,9 @@ def test_roofline_uses_measured_peaks_and_payload_is_half_of_copy():
     p = R.measured_peaks()
     assert p["hbm_gbs"] > 1000 and p["_source"] in ("measured", "fallback")
     assert R.copy_roofline_gbps({"hbm_gbs": 6578.7}) == 6578.7 / 2
-    # fused pack: 2 B read + 3 x (1 + 1/32) B moved per 2 B of source
+    # fused pack: the algorithmic bytes -- 2 B read + (1 + 1/32) B written per 2 B of source (no fraction above 1 any more)
     src = R.fused_pack_roofline_gbps({"hbm_gbs": 6578.7})
-    assert abs(src - 6578.7 * 2 / (2 + 3 * 33 / 32)) < 1e-6
+    assert abs(src - 6578.7 * 2 / (2 + 33 / 32)) < 1e-6
     assert R.fused_pack_roofline_gbps({"hbm_gbs": 6578.7}, wire_gbs=50.0) == 50.0 * 2 / (33 / 32)   # NIC-bound on a real wire
     assert R.fraction(50.0, 100.0) == 0.5
 

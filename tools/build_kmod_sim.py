@@ -40,5 +40,25 @@ def build(force: bool = False) -> Path:
     return lib
 
 
+def build_stress(sanitizer: str = "address") -> Path:
+    """kmod/tests/sim_stress.c + both modules + the simulation runtime as ONE executable under a sanitizer
+    ("address" or "thread"; TSan needs the whole program instrumented, so this is not the shared library)."""
+    out = KMOD / f"sim_stress_{sanitizer}"
+    srcs = [(KMOD / "b200p2p.c", "b200p2p"), (KMOD / "b200p2ptest.c", "b200p2ptest"), (KMOD / "shim" / "sim_runtime.c", "sim"),
+            (KMOD / "tests" / "sim_stress.c", "stress")]
+    deps = [s for s, _ in srcs] + list((KMOD / "shim").rglob("*.h")) + list((KMOD / "include").glob("*.h"))
+    if out.exists() and all(out.stat().st_mtime >= d.stat().st_mtime for d in deps):
+        return out
+    san = [f"-fsanitize={sanitizer}", "-fno-omit-frame-pointer"]
+    flags = [f for f in FLAGS if f != "-fvisibility=hidden"] + san
+    objs = []
+    for src, mod in srcs:
+        obj = KMOD / f".{mod}.stress_{sanitizer}.o"
+        subprocess.run(["gcc", *flags, f"-DKBUILD_MODNAME={mod}", "-c", str(src), "-o", str(obj)], check=True)
+        objs.append(str(obj))
+    subprocess.run(["gcc", "-o", str(out), *objs, *san, "-lpthread"], check=True)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv))
