@@ -683,6 +683,203 @@ gemm_send2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   }
 }
 
+// ------------------------------------------------------------------ wide variant: 256x256 per CTA, 512x256 per CTA pair
+// What ncu showed against cuBLAS at 8192^3 (profiles/ncu/gemm_vs_cublas_*): the pair kernel above needs 1.4 % more
+// cycles than nvjet_tst_256x256_64x4_2x1_2cta -- and runs them at 1.43 GHz where the library holds 1.50 GHz: the box
+// is power-limited, and the pair kernel moves 1.7x the L2 -> SM bytes (252 M vs 149 M sectors) for the same FLOPs.
+// The library's shape is 256 rows of A per CTA: per 64-deep k-block a CTA loads 32 KiB of A and its 16 KiB half of
+// B for TWO M=256 pair-MMAs (rows 0-127 and 128-255 of each CTA, accumulators in TMEM columns 0-255 and 256-511),
+// i.e. 48 KiB per 8.4 MFLOP instead of 32 KiB per 4.2: a quarter less operand traffic, half the barrier and TMA
+// operations per FLOP.  TMEM is then single-buffered (512 columns = one 256x256 fp32 tile), so the epilogue hands the
+// two halves back separately: the next tile's MMAs on columns 0-255 start while columns 256-511 are still being
+// drained, and the TMA producer keeps prefetching the next tile's stages throughout (the kernel is persistent,
+// unlike the library's one-tile CTAs).
+constexpr int STAGES3 = 4;
+constexpr int A3_STAGE = 2 * A_STAGE;           // 256 rows x 64: 32 KiB
+struct alignas(1024) Smem3 {
+  uint8_t a[STAGES3][A3_STAGE];
+  uint8_t b[STAGES3][BH_STAGE];
+  uint8_t stage_c[4][2][kStageC];
+  alignas(8) uint64_t full[STAGES3], empty[STAGES3], tfull, tempty[2];
+  uint32_t tmem_base;
+  volatile int abort;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_send3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const __grid_constant__ CUtensorMap tmap_c, GemmArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  Smem3& s = *reinterpret_cast<Smem3*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();
+  const bool leader = rank == 0;
+  const unsigned long long t_start = globaltimer_ns();
+  const uint32_t mq_blks = g.M / (4 * BM), n_blks = g.N / BN, k_blks = g.K / BK;
+  const uint32_t n_tiles = mq_blks * n_blks, n_clusters = gridDim.x / 2, cluster_id = blockIdx.x / 2;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES3; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    mbar_init(&s.tfull, 1);
+    mbar_init(&s.tempty[0], 8); mbar_init(&s.tempty[1], 8);
+    s.abort = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&s.tmem_base)), "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = s.tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs: own 256 rows of A, own half of B)
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (uint32_t tile = cluster_id; tile < n_tiles && !s.abort; tile += n_clusters) {
+        uint32_t mq, n_blk;
+        tile_coords(tile, mq_blks, n_blks, g.group_m, &mq, &n_blk);
+        for (uint32_t kb = 0; kb < k_blks; ++kb) {
+          if (!mbar_wait_t(s, &s.empty[stage], phase ^ 1)) goto producer3_done;
+          const uint32_t lbar = mapa(s32(&s.full[stage]), 0);
+          if (leader) mbar_expect_tx(&s.full[stage], 2 * (A3_STAGE + BH_STAGE));
+          tma_load_2d_2sm(s.a[stage], &tmap_a, lbar, (int)(kb * BK), (int)(mq * 4 * BM + rank * 2 * BM));
+          tma_load_2d_2sm(s.b[stage], &tmap_b, lbar, (int)(kb * BK), (int)(n_blk * BN + rank * (BN / 2)));
+          if (++stage == STAGES3) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  producer3_done:
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only): two M=256 pair-MMAs per k16, one per accumulator half
+    if (leader && lane == 0) {
+      uint32_t stage = 0, phase = 0, tphase = 0;
+      for (uint32_t tile = cluster_id; tile < n_tiles && !s.abort; tile += n_clusters) {
+        for (uint32_t kb = 0; kb < k_blks; ++kb) {
+          if (!mbar_wait_t(s, &s.full[stage], phase)) goto mma3_done;
+          tc_fence_after();
+          const uint64_t db = smem_desc(s.b[stage]);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (kb == 0) {                                                     // this half has been drained by both CTAs' epilogues
+              if (!mbar_wait_t(s, &s.tempty[h], tphase ^ 1)) goto mma3_done;
+              tc_fence_after();
+            }
+            const uint64_t da = smem_desc(s.a[stage] + h * A_STAGE);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_f16_2sm(tmem_base + (uint32_t)h * BN, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc2, (kb | (uint32_t)k) != 0);
+          }
+          tc_commit_2sm(&s.empty[stage]);
+          if (++stage == STAGES3) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_2sm(&s.tfull);                                               // both halves complete, in BOTH CTAs
+        tphase ^= 1;
+      }
+    }
+  mma3_done:
+    __syncwarp();
+  } else {
+    // ===================== epilogue (both CTAs: their own 256 rows = two 128-row panels of the tile)
+    const uint32_t q = warp & 3;
+    uint32_t tphase = 0;
+    const bool sys = g.qp != nullptr && poster_sys(g.qp);
+    uint32_t pending0 = ~0u, pending1 = ~0u;
+    for (uint32_t tile = cluster_id; tile < n_tiles; tile += n_clusters) {
+      uint32_t mq, n_blk;
+      tile_coords(tile, mq_blks, n_blks, g.group_m, &mq, &n_blk);
+      if (!mbar_wait_t(s, &s.tfull, tphase)) break;
+      tphase ^= 1;
+      tc_fence_after();
+#pragma unroll 1
+      for (uint32_t h = 0; h < 2; ++h) {
+        const uint32_t m_blk = mq * 4 + rank * 2 + h;                          // 128-row panel index
+        const uint32_t taddr = tmem_base + ((q * 32u) << 16) + h * BN;
+        if (!g.out_fp8) {
+          epilogue_rows_tma(s.stage_c[q], &tmap_c, taddr, (int)(n_blk * BN), (int)(m_blk * BM + q * 32), lane);
+        } else {
+          const uint32_t row_in_panel = q * 32 + lane;
+          uint8_t* rec = reinterpret_cast<uint8_t*>(g.c) + (uint64_t)m_blk * panel_record_bytes(g.N);
+          uint8_t* qrow = rec + (size_t)row_in_panel * g.N + (size_t)n_blk * BN;
+          uint8_t* srow = rec + (size_t)BM * g.N + (size_t)row_in_panel * (g.N / 32) + (size_t)n_blk * (BN / 32);
+#pragma unroll 2
+          for (int c = 0; c < BN / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld32(taddr + c * 32, r);
+            tmem_ld_wait();
+            quantize_block(r, reinterpret_cast<uint4*>(qrow + c * 32), srow + c);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {                                                       // 8 arrivals (4 warps x 2 CTAs) on the LEADER's barrier
+          if (leader) mbar_arrive(&s.tempty[h]);
+          else mbar_arrive_remote(mapa(s32(&s.tempty[h]), 0));
+        }
+      }
+      if (g.qp != nullptr) {
+        // panel accounting, one tile late for the staged TMA stores (see the pair kernel)
+        if (!g.out_fp8) {
+          if (pending0 != ~0u) {
+            if (lane == 0) bulk_wait_keep4();
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+            if (threadIdx.x == 64) { panel_tile_done(g, pending0, n_blks, sys); panel_tile_done(g, pending1, n_blks, sys); }
+          }
+          pending0 = mq * 4 + rank * 2; pending1 = pending0 + 1;
+        } else {
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+          if (threadIdx.x == 64) { panel_tile_done(g, mq * 4 + rank * 2, n_blks, sys); panel_tile_done(g, mq * 4 + rank * 2 + 1, n_blks, sys); }
+        }
+      }
+    }
+    if (lane == 0) bulk_wait_all();
+    if (pending0 != ~0u && !s.abort) {
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      if (threadIdx.x == 64) { panel_tile_done(g, pending0, n_blks, sys); panel_tile_done(g, pending1, n_blks, sys); }
+    }
+  }
+
+  // ===================== teardown
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+  }
+  if (threadIdx.x == 64) {
+    if (s.abort) g.out[0] = (unsigned long long)(long long)WAIT_TIMEOUT;
+    fence_gpu();
+    unsigned int old = atomicAdd(&g.counters[g.M / BM], 1u);
+    if (old + 1 == gridDim.x) {
+      const unsigned long long t_compute_end = globaltimer_ns();
+      fence_gpu();
+      unsigned long long posted = ld_u64_volatile(&g.acc[1]);
+      if (g.qp != nullptr) {
+        int rc = WAIT_TIMEOUT;
+        unsigned long long fidx = sq_reserve(g.qp, 1, g.timeout_ns);
+        if (fidx != ~0ull) {
+          uint8_t* slot = g.qp->sq + ((fidx & ((1ull << g.qp->sq_log) - 1)) << 6);
+          st_v4(slot + 0, ctrl_word0(OP_NOP, (uint16_t)fidx), ctrl_word1(g.qp->qpn, 1), (uint32_t)CTRL_CQ_UPDATE << 24, 0u);
+          st_v4(slot + 16, 0u, 0u, 0u, 0u); st_v4(slot + 32, 0u, 0u, 0u, 0u); st_v4(slot + 48, 0u, 0u, 0u, 0u);
+          if (sq_submit(g.qp, fidx, 1, g.timeout_ns, true) == WAIT_OK) rc = g.post_only ? WAIT_OK : sq_wait(g.qp, fidx, g.timeout_ns);
+        }
+        if (posted != g.M / BM && rc == WAIT_OK) rc = WAIT_TIMEOUT;
+        if (rc != WAIT_OK) g.out[0] = (unsigned long long)(long long)rc;
+      }
+      g.out[1] = t_start; g.out[2] = globaltimer_ns(); g.out[3] = posted;
+      g.out[4] = ~ld_u64_volatile(&g.acc[2]); g.out[5] = t_compute_end; g.out[6] = 3;   // [6] = variant used
+      g.counters[g.M / BM] = 0;
+      g.acc[0] = 0; g.acc[1] = 0; g.acc[2] = 0;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ host: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -741,6 +938,23 @@ RN_API int rn_k_gemm_send(uint64_t stream, int grid, uint64_t a, uint64_t b, uin
   unsigned long long* o = (unsigned long long*)out_dev;
   for (int i = 0; i < 8; ++i) o[i] = 0;
   if (grid <= 0) grid = 148;
+  // cta_group: 1 = single-CTA kernel, 2 = pair kernel (256x256 per pair), 3 = wide pair kernel (512x256 per pair),
+  // 0 = the widest the shape allows.  The wide kernel has no plain-store / probe epilogues and no direct mode.
+  const bool wide_ok = (M % (4 * BM)) == 0 && grid >= 2 && !(flags & (kFlagPlainStores | kFlagDenseProbe | kFlagDirect));
+  if ((cta_group == 3 || cta_group == 0) && wide_ok) {
+    rc = make_map(&ma, (const void*)a, M, K, 2 * BM);                 // 256 rows of A per CTA in one box
+    if (!rc) rc = make_map(&mb, (const void*)b, N, K, BN / 2);
+    if (rc) return rc;
+    const uint32_t n_tiles = (M / (4 * BM)) * (N / BN);
+    grid &= ~1;
+    if ((uint32_t)grid > 2 * n_tiles) grid = (int)(2 * n_tiles);
+    if (g.group_m > 1) g.group_m = (g.group_m + 1) / 2;              // group_m is given in 256-row units; tiles here are 512 rows
+    const size_t smem = sizeof(Smem3) + 1024;
+    cudaError_t e = cudaFuncSetAttribute(gemm_send3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return -(int)e - 1000;
+    gemm_send3_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ma, mb, mc, g);
+    return (int)cudaGetLastError();
+  }
   const bool two = cta_group != 1 && (M % (2 * BM)) == 0 && grid >= 2;
   if (two) {
     // pairs of CTAs share a 256x256 tile: B map delivers half tiles (128 rows)
@@ -770,5 +984,7 @@ extern "C" __attribute__((visibility("default"))) void rn_preload_gemm() {
   cudaFuncSetAttribute(gemm_send_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Smem) + 1024));
   cudaFuncGetAttributes(&at, gemm_send2_kernel);
   cudaFuncSetAttribute(gemm_send2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Smem2) + 1024));
+  cudaFuncGetAttributes(&at, gemm_send3_kernel);
+  cudaFuncSetAttribute(gemm_send3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Smem3) + 1024));
   encode_tiled();
 }

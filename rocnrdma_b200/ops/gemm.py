@@ -83,9 +83,9 @@ def gemm_send(ctx, a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, c_mr=None,
     peer region as seen locally, ``dst_mr``).
     ``plain_stores``: bf16 epilogue with per-thread row stores instead of staged TMA tensor stores (A/B switch).
     ``group_m``: M blocks that advance together across N (L2 reuse of B; 0 = 8 for compute only, 4 when sending).
-    ``cta_group``: 2 = CTA-pair kernel (256x256 tiles, the B operand shared across the pair; measured
-    1.05-1.11x cuBLAS at 4096^3 .. 16384x4096x1024), 1 = single-CTA 128x256 kernel, 0 (default) = the pair
-    kernel whenever M % 256 == 0.
+    ``cta_group``: 3 = wide CTA-pair kernel (512x256 per pair, 256 rows of A per CTA, the shape cuBLAS's nvjet
+    kernels use), 2 = CTA-pair kernel (256x256 per pair), 1 = single-CTA 128x256 kernel, 0 (default) = the widest
+    the shape allows (M % 512, M % 256).
     """
     for t in (a, b):
         assert t.dtype == torch.bfloat16 and t.is_contiguous()
@@ -102,7 +102,10 @@ def gemm_send(ctx, a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, c_mr=None,
     if qp is not None and (c_mr is None or dst_mr is None):
         raise ValueError("sending needs c_mr (registration of c) and dst_mr")
     if cta_group == 0:
-        cta_group = 2 if M % (2 * BM) == 0 else 1
+        wide_ok = M % (4 * BM) == 0 and not direct and not plain_stores and not os.environ.get("RN_GEMM_DENSE_PROBE")
+        cta_group = 3 if wide_ok else (2 if M % (2 * BM) == 0 else 1)
+    if os.environ.get("RN_GEMM_CTA_GROUP"):            # A/B switch for benchmarks
+        cta_group = int(os.environ["RN_GEMM_CTA_GROUP"])
     if group_m == 0:
         # tile rasterisation: M blocks (pairs for cta_group 2) that advance together across N; more = better
         # L2 reuse of B, fewer = panels complete (and are sent) more evenly

@@ -174,3 +174,50 @@ def test_gemm_epilogue_variants_agree_bit_for_bit(ctx, cta_group):
     assert torch.equal(c1, c2)
     ref = a.float() @ b.float().t()
     assert (c1.float() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 256, 64), (512, 512, 256), (1024, 768, 320), (2048, 1024, 1024)])
+def test_gemm_wide_pair_kernel_matches_fp32_reference(ctx, M, N, K):
+    """cta_group=3: 256 rows of A per CTA, two M=256 pair-MMAs per k16 into the two halves of TMEM."""
+    a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    b = torch.randn(N, K, device="cuda").to(torch.bfloat16)
+    c = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    r = ops.gemm_send(ctx, a, b, c, cta_group=3)
+    assert r.ok, r.status
+    ref = a.float() @ b.float().T
+    assert torch.allclose(c.float(), ref, rtol=2e-2, atol=0.5 * (K / 256) ** 0.5)
+
+
+def test_gemm_wide_identity_layout(ctx):
+    """B = I: C must equal A exactly -- every row of every half of every CTA lands where it belongs."""
+    M = N = K = 1024
+    a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    b = torch.eye(N, K, device="cuda").to(torch.bfloat16)
+    c = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    assert ops.gemm_send(ctx, a, b, c, cta_group=3, grid=6).ok          # 3 clusters over 8 tiles: uneven, several tiles per cluster
+    assert torch.equal(c, a)
+
+
+@pytest.mark.parametrize("out_fp8", [False, True])
+def test_gemm_wide_send_panels(ctx, out_fp8):
+    M, N, K = 1024, 512, 256
+    a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    b = torch.randn(N, K, device="cuda").to(torch.bfloat16)
+    if out_fp8:
+        nb = (M // 128) * ops.gemm.panel_record_bytes(N)
+        c = torch.zeros(nb, dtype=torch.uint8, device="cuda")
+    else:
+        c = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    d = torch.zeros_like(c)
+    cm, dm = ctx.reg_mr(c), ctx.reg_mr(d)
+    qp = ctx.loopback_qp(depth=64)
+    ctx.engine_start(ctas=8, idle_timeout_ms=3000)
+    r = ops.gemm_send(ctx, a, b, c, c_mr=cm, qp=qp, dst_mr=dm, cta_group=3, out_fp8=out_fp8, signal_every=2)
+    ctx.engine_stop()
+    assert r.ok and r.panels_posted == M // 128, (r.status, r.panels_posted)
+    assert torch.equal(c, d)
+    ref = a.float() @ b.float().T
+    if out_fp8:
+        assert torch.equal(d, ops.gemm.ref_fp8_panels(ref)) or torch.allclose(ops.gemm.dequant_fp8_panels(d, M, N), ref, rtol=0.08, atol=0.5)
+    else:
+        assert torch.allclose(d.float(), ref, rtol=2e-2, atol=0.5)

@@ -17,6 +17,8 @@ ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
 kw = {}
 if os.environ.get("RN_GROUP_M"):
     kw["group_m"] = int(os.environ["RN_GROUP_M"])
+if os.environ.get("RN_CTA_GROUP"):
+    kw["cta_group"] = int(os.environ["RN_CTA_GROUP"])
 for (M, N, K), (a, b, c) in bufs.items():
     flops = 2.0 * M * N * K
     res = {}
