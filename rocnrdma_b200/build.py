@@ -26,6 +26,7 @@ CUDA_SOURCES = [
     "kernels/rdma_ops.cu",
     "kernels/pack_fp8.cu",
     "kernels/gemm_send.cu",
+    "kernels/gemm_mxfp8.cu",
 ]
 CXX_SOURCES = [
     "reg/registration.cc",

@@ -148,9 +148,12 @@ bool legal_transition(uint32_t from, uint32_t to) {
 // time while the engine runs would only start after the engine's watchdog exit
 // (observed on B200 / driver 580.159; see DESIGN.md "engine residency rules").
 extern "C" {
+uint64_t rn_gemm_workspace_bytes() __attribute__((weak));
+void rn_gemm_set_workspace(int dev, uint64_t ptr) __attribute__((weak));
 void rn_preload_rdma_ops() __attribute__((weak));
 void rn_preload_pack() __attribute__((weak));
 void rn_preload_gemm() __attribute__((weak));
+void rn_preload_gemm_mx() __attribute__((weak));
 }
 static void preload_all_kernels() {
   cudaFuncAttributes a;
@@ -158,6 +161,7 @@ static void preload_all_kernels() {
   if (rn_preload_rdma_ops) rn_preload_rdma_ops();
   if (rn_preload_pack) rn_preload_pack();
   if (rn_preload_gemm) rn_preload_gemm();
+  if (rn_preload_gemm_mx) rn_preload_gemm_mx();
   cudaGetLastError();
 }
 
@@ -207,6 +211,17 @@ RN_API int rn_hca_open(int dev, uint32_t max_mkeys, uint32_t max_qps, uint64_t a
   h->dscratch_size = 1 << 20;
   h->dscratch = (uint8_t*)arena_alloc(h, h->dscratch_size, false);
   h->mrs.resize(h->max_mkeys);
+  if (rn_gemm_workspace_bytes && rn_gemm_set_workspace) {
+    // stream-K workspace of the wide GEMM kernel (one per device, shared by every context on it; never freed: a
+    // later context may still be launching GEMMs that use it)
+    static void* ws_by_dev[16] = {};
+    if (dev < 16 && !ws_by_dev[dev]) {
+      const size_t n = (size_t)rn_gemm_workspace_bytes();
+      if (cudaMalloc(&ws_by_dev[dev], n) == cudaSuccess) cudaMemsetAsync(ws_by_dev[dev], 0, n, h->ctl);
+      else { ws_by_dev[dev] = nullptr; cudaGetLastError(); }
+    }
+    if (dev < 16) rn_gemm_set_workspace(dev, (uint64_t)ws_by_dev[dev]);
+  }
   preload_all_kernels();
   CU_OK(cudaStreamSynchronize(h->ctl));
   *out = h;

@@ -318,6 +318,28 @@ __device__ __forceinline__ int poster_poll(Poster& p, int max_cqes = 8) {
   }
   return rc < 0 ? rc : n;
 }
+// Split poll: issue the load of the next CQE's tail now, look at it later.  A poster that interleaves
+//     build WQE -> poster_peek -> poster_ring (release + doorbell) -> poster_take
+// has the CQE load in flight while the release in front of the doorbell waits for the WQE stores to be acknowledged:
+// the two L2 round trips of a post-one / poll-one iteration overlap instead of adding up.
+__device__ __forceinline__ uint4 poster_peek(const Poster& p) {
+  return ld_v4_volatile(p.cq_buf + ((size_t)(p.ci & ((1u << p.cq_log) - 1)) << 6) + 48);
+}
+// Consume the CQE whose tail was loaded by poster_peek, if it was ready and ours.  Returns 1 / 0 / WAIT_CQE_ERROR.
+__device__ __forceinline__ int poster_take(Poster& p, const uint4 tail) {
+  const uint8_t op_own = (uint8_t)(tail.w >> 24);
+  if (!cqe_valid(op_own, p.ci, p.cq_log)) return 0;
+  const uint8_t opc = cqe_opcode(op_own);
+  if ((opc != CQE_REQ && opc != CQE_REQ_ERR) || (be32(tail.z) & 0xffffffu) != p.qpn) return 0;
+  const uint16_t wqe_counter = be16((uint16_t)(tail.w & 0xffff));
+  p.cons += (unsigned long long)((uint16_t)(wqe_counter + 1 - (uint16_t)p.cons));
+  if (p.trace) trace_stamp(p.qp, p.cons - 1, TR_SEEN);
+  ++p.ci;
+  __threadfence();                                                // acquire: payload behind the CQE
+  st_u32_volatile(&p.cq->dbrec[0], be32(p.ci & 0xffffff));
+  return opc == CQE_REQ_ERR ? WAIT_CQE_ERROR : 1;
+}
+
 // Block until WQE `idx` completed (or timeout / error).
 __device__ __forceinline__ int poster_wait(Poster& p, unsigned long long idx, unsigned long long timeout_ns) {
   int err = WAIT_OK;

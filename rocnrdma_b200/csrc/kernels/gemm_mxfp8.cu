@@ -1,0 +1,372 @@
+// K7: block-scaled fp8 GEMM that CONSUMES what K3 / K4 put on the wire.
+//
+//   C[M,N] (bf16) = dequant(A) * dequant(B)^T,   A = (A_q [M,K] e4m3, A_s [M,K/32] UE8M0),  B likewise [N,K]
+//
+// with the dequantisation done by the tensor core: tcgen05.mma.kind::mxf8f6f4.block_scale multiplies every
+// 32-element block of K by 2^(scale - 127) for its row of A and its row of B while it accumulates in fp32.  The
+// operands are exactly the self-contained records the send side produces -- pack_fp8.cu chunk records
+// ([elems fp8][elems/32 scales]) and gemm_send.cu panel records ([128 x N fp8][128 x N/32 scales]) -- so a receiver
+// can multiply straight out of its registered receive buffer: no dequantisation pass, half the HBM bytes of bf16
+// operands, and (nominally) twice the tensor rate.  Round 1 had an fp8 EPILOGUE only; its records could be produced
+// but never consumed by a GEMM.
+//
+// One CTA per SM, persistent, 320 threads:
+//   warp 0      TMA producer: 3-D tensor maps (K, rows-in-record, record) so an operand may live inside records;
+//               128 x 128-byte boxes, SWIZZLE_128B, out-of-bounds rows / K filled with zeros (ragged shapes)
+//   warp 1      MMA issuer: per 128-deep k-block two tcgen05.cp 32x128b.warpx4 copy the block's scale factors from
+//               shared memory into TMEM (4 columns each for A and B), then four K=32 MMAs read them by scale-factor
+//               id; accumulators double-buffered in TMEM columns 0-255, scale factors ring through columns 256+
+//   warps 2-5   epilogue: tcgen05.ld 32x32b.x32 -> bf16 -> bounds-checked row stores
+//   warps 6-9   scale loaders: each thread owns one row of the A tile and one of the B tile and lays their four
+//               scale bytes of the k-block into the 512-byte chunk layout the hardware expects
+//               (byte (r % 32) * 16 + (r / 32) * 4 + k: 32 rows of 16 bytes, replicated to the four lane quarters)
+// Layout facts (instruction-descriptor bits, scale-factor chunk, UTCCP shape) were read off the CUTLASS headers
+// vendored in the image (cute/arch/mma_sm100_desc.hpp, cutlass/detail/sm100_blockscaled_layout.hpp); no CUTLASS code
+// is compiled in.  No counterpart in the reference.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../hca/post.cuh"
+
+using namespace rn;
+using namespace rn::dev;
+
+#define RN_API extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 128, UMMA_K = 32, STAGES = 4;
+constexpr int A_STAGE = BM * BK, B_STAGE = BN * BK;            // 16 KiB each (one byte per element)
+constexpr int SF_STAGE = 512;                                  // 128 rows x 4 scale bytes, chunk layout
+constexpr int kThreads = 320;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kSfCol0 = 256;                              // scale factors live above the two 128-column accumulators
+constexpr unsigned long long kWaitNs = 2000000000ull;
+
+struct alignas(1024) Smem {
+  uint8_t a[STAGES][A_STAGE];
+  uint8_t b[STAGES][B_STAGE];
+  alignas(128) uint8_t sfa[STAGES][SF_STAGE];
+  alignas(128) uint8_t sfb[STAGES][SF_STAGE];
+  alignas(8) uint64_t full[STAGES], empty[STAGES], tfull[2], tempty[2];
+  uint32_t tmem_base;
+  volatile int abort;
+};
+
+struct MxArgs {
+  const uint8_t* a_s;        // scales of A: row r of record i at a_s + i * a_rec_stride + r * (K / 32)
+  const uint8_t* b_s;
+  uint64_t a_rec_stride, b_rec_stride;   // bytes between records (fp8 block and scale block move together)
+  uint32_t a_rows_per_rec, b_rows_per_rec;
+  __nv_bfloat16* c;
+  uint32_t M, N, K;
+  unsigned long long* out;   // [status, t_start, t_end, tiles, 0...]
+};
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(n)); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory"); }
+__device__ __forceinline__ bool mbar_try(uint64_t* b, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(s32(b)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_wait(Smem& s, uint64_t* b, uint32_t parity) {
+  if (mbar_try(b, parity)) return true;
+  unsigned long long t0 = globaltimer_ns();
+  unsigned n = 0;
+  while (!mbar_try(b, parity)) {
+    if ((++n & 255) == 0) {
+      if (s.abort) return false;
+      if (globaltimer_ns() - t0 > kWaitNs) { s.abort = 1; return false; }
+    }
+  }
+  return true;
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(s32(smem_dst)), "l"(map), "r"(s32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+}
+// K-major, SWIZZLE_128B operand tile of one-byte elements: 128-byte rows (128 elements), 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t smem_desc_sw128(const void* p) {
+  uint64_t d = (uint64_t)((s32(p) & 0x3ffff) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Scale-factor chunk for tcgen05.cp 32x128b: 32 rows of 16 bytes, no swizzle; 8-row core matrices 128 bytes apart.
+__device__ __forceinline__ uint64_t smem_desc_sf(const void* p) {
+  uint64_t d = (uint64_t)((s32(p) & 0x3ffff) >> 4);
+  d |= (uint64_t)(16 >> 4) << 16;                          // leading-dimension byte offset (one core matrix wide: unused)
+  d |= (uint64_t)(128 >> 4) << 32;                         // stride between 8-row core matrices
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+__device__ __forceinline__ void utccp_32x128b_warpx4(uint32_t tmem_dst, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(tmem_dst), "l"(sdesc) : "memory");
+}
+// kind::mxf8f6f4 block-scaled instruction descriptor: A = B = e4m3 (format 0), both K-major, UE8M0 scales,
+// N at [17,23) in units of 8, M at [24,29) in units of 16, scale-factor ids at [4,6) (B) and [29,31) (A), K = 32.
+__device__ __forceinline__ uint32_t mx_idesc(uint32_t sf_id) {
+  return (sf_id << 4) | ((uint32_t)(BN >> 3) << 17) | (1u << 23) | ((uint32_t)(BM >> 4) << 24) | (sf_id << 29);
+}
+__device__ __forceinline__ void umma_mxf8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t tsfa, uint32_t tsfb, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
+               ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(tsfa), "r"(tsfb) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+               "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                 "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                 "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t pack_bf16(uint32_t lo, uint32_t hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(__uint_as_float(lo), __uint_as_float(hi));
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// the four UE8M0 bytes of k-block kb for global row `row` of an operand (127 = 2^0 beyond the matrix: the data
+// there is zero-filled by TMA, so any finite scale gives 0)
+__device__ __forceinline__ uint32_t load_scales(const uint8_t* base, uint64_t rec_stride, uint32_t rows_per_rec, uint32_t rows, uint32_t ks,
+                                                uint32_t row, uint32_t kb) {
+  if (row >= rows) return 0x7f7f7f7fu;
+  const uint8_t* p = base + (uint64_t)(row / rows_per_rec) * rec_stride + (uint64_t)(row % rows_per_rec) * ks + (uint64_t)kb * 4;
+  if (kb * 4 + 4 <= ks && ((uintptr_t)p & 3) == 0) return *reinterpret_cast<const uint32_t*>(p);
+  uint32_t v = 0;
+#pragma unroll
+  for (uint32_t i = 0; i < 4; ++i) v |= (uint32_t)(kb * 4 + i < ks ? p[i] : 0x7f) << (8 * i);
+  return v;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, MxArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  Smem& s = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned long long t_start = globaltimer_ns();
+  const uint32_t m_blks = (g.M + BM - 1) / BM, n_blks = (g.N + BN - 1) / BN, k_blks = (g.K + BK - 1) / BK;
+  const uint32_t n_tiles = m_blks * n_blks, ks = g.K / 32;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&s.full[i], 1 + 4); mbar_init(&s.empty[i], 1); }   // TMA transaction + 4 scale-loader warps
+    for (int i = 0; i < 2; ++i) { mbar_init(&s.tfull[i], 1); mbar_init(&s.tempty[i], 4); }
+    s.abort = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&s.tmem_base)), "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s.tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (uint32_t tile = blockIdx.x; tile < n_tiles && !s.abort; tile += gridDim.x) {
+        const uint32_t m_blk = tile / n_blks, n_blk = tile % n_blks;
+        const uint32_t ar = m_blk * BM, br = n_blk * BN;
+        for (uint32_t kb = 0; kb < k_blks; ++kb) {
+          if (!mbar_wait(s, &s.empty[stage], phase ^ 1)) goto producer_done;
+          mbar_expect_tx(&s.full[stage], A_STAGE + B_STAGE);
+          // rows of a tile never straddle records (rows_per_rec is a multiple of 128, or the operand is one record)
+          tma_load_3d(s.a[stage], &tmap_a, &s.full[stage], (int)(kb * BK), (int)(ar % g.a_rows_per_rec), (int)(ar / g.a_rows_per_rec));
+          tma_load_3d(s.b[stage], &tmap_b, &s.full[stage], (int)(kb * BK), (int)(br % g.b_rows_per_rec), (int)(br / g.b_rows_per_rec));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  producer_done:
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (uint32_t tile = blockIdx.x; tile < n_tiles && !s.abort; tile += gridDim.x) {
+        if (!mbar_wait(s, &s.tempty[acc], acc_phase ^ 1)) goto mma_done;
+        tc_fence_after();
+        const uint32_t d = tmem_base + acc * BN;
+        for (uint32_t kb = 0; kb < k_blks; ++kb) {
+          if (!mbar_wait(s, &s.full[stage], phase)) goto mma_done;             // A, B landed and the scale chunks are written
+          tc_fence_after();
+          const uint32_t tsfa = tmem_base + kSfCol0 + stage * 8, tsfb = tsfa + 4;
+          utccp_32x128b_warpx4(tsfa, smem_desc_sf(s.sfa[stage]));              // copies and MMAs execute in issue order
+          utccp_32x128b_warpx4(tsfb, smem_desc_sf(s.sfb[stage]));
+          const uint64_t da = smem_desc_sw128(s.a[stage]), db = smem_desc_sw128(s.b[stage]);
+#pragma unroll
+          for (uint32_t k = 0; k < BK / UMMA_K; ++k)                            // +32 bytes along K = +2 in the address field
+            umma_mxf8(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), mx_idesc(k), tsfa | (k << 30), tsfb | (k << 30), (kb | k) != 0);
+          tc_commit(&s.empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&s.tfull[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  mma_done:
+    __syncwarp();
+  } else if (warp < 6) {
+    // ===================== epilogue
+    const uint32_t q = warp & 3;                                               // TMEM lane quarter this warp may read
+    uint32_t acc = 0, acc_phase = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const uint32_t m_blk = tile / n_blks, n_blk = tile % n_blks;
+      if (!mbar_wait(s, &s.tfull[acc], acc_phase)) break;
+      tc_fence_after();
+      const uint32_t row = m_blk * BM + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * BN;
+      __nv_bfloat16* crow = g.c + (size_t)row * g.N + (size_t)n_blk * BN;
+#pragma unroll 2
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+        const uint32_t col0 = n_blk * BN + c * 32;
+        if (row < g.M && col0 < g.N) {
+          if (col0 + 32 <= g.N && (g.N & 7) == 0) {
+            uint4* dst = reinterpret_cast<uint4*>(crow + c * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              dst[j] = make_uint4(pack_bf16(r[8 * j], r[8 * j + 1]), pack_bf16(r[8 * j + 2], r[8 * j + 3]), pack_bf16(r[8 * j + 4], r[8 * j + 5]),
+                                  pack_bf16(r[8 * j + 6], r[8 * j + 7]));
+          } else {
+            for (int j = 0; j < 32 && col0 + j < g.N; ++j) crow[c * 32 + j] = __float2bfloat16_rn(__uint_as_float(r[j]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ===================== scale loaders (warps 6-9): thread (w, lane) owns tile row w * 32 + lane of A and of B
+    const uint32_t w = warp - 6;
+    uint32_t stage = 0, phase = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles && !s.abort; tile += gridDim.x) {
+      const uint32_t m_blk = tile / n_blks, n_blk = tile % n_blks;
+      const uint32_t arow = m_blk * BM + w * 32 + lane, brow = n_blk * BN + w * 32 + lane;
+      for (uint32_t kb = 0; kb < k_blks; ++kb) {
+        const uint32_t va = load_scales(g.a_s, g.a_rec_stride, g.a_rows_per_rec, g.M, ks, arow, kb);
+        const uint32_t vb = load_scales(g.b_s, g.b_rec_stride, g.b_rows_per_rec, g.N, ks, brow, kb);
+        if (!mbar_wait(s, &s.empty[stage], phase ^ 1)) goto loader_done;
+        *reinterpret_cast<uint32_t*>(&s.sfa[stage][lane * 16 + w * 4]) = va;
+        *reinterpret_cast<uint32_t*>(&s.sfb[stage][lane * 16 + w * 4]) = vb;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // generic-proxy writes -> visible to tcgen05.cp
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s.full[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  loader_done:
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+  }
+  if (threadIdx.x == 64) {
+    if (s.abort) g.out[0] = (unsigned long long)(long long)WAIT_TIMEOUT;
+    if (blockIdx.x == 0) { g.out[1] = t_start; g.out[3] = n_tiles; }
+    __threadfence();
+    atomicMax(&g.out[2], globaltimer_ns());
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+// fp8 operand [rows, K] held in n_rec records of rows_per_rec rows, rec_stride bytes apart: a 3-D map (K, row, record)
+int make_map3(CUtensorMap* m, const void* base, uint64_t rows, uint64_t K, uint64_t rows_per_rec, uint64_t rec_stride) {
+  EncodeTiledFn fn = encode_tiled();
+  if (!fn) return -38;
+  const uint64_t n_rec = (rows + rows_per_rec - 1) / rows_per_rec;
+  cuuint64_t dims[3] = {K, rows_per_rec < rows ? rows_per_rec : rows, n_rec};
+  cuuint64_t strides[2] = {K, rec_stride};
+  cuuint32_t box[3] = {BK, BM, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -(int)r - 2000;
+}
+
+}  // namespace
+
+// a_q / b_q: fp8 e4m3 bytes; a_s / b_s: UE8M0 scale bytes (one per 32 elements of K); *_rows_per_rec / *_rec_stride
+// describe operands that live inside K3 chunk records or K4 panel records (rows_per_rec = rows and any stride for a
+// plain matrix).  K % 32 == 0, K % 16 == 0 for the TMA row stride; M and N are free (bf16 C rows of N elements).
+RN_API int rn_k_gemm_mxfp8(uint64_t stream, int grid, uint64_t a_q, uint64_t a_s, uint32_t a_rows_per_rec, uint64_t a_rec_stride, uint64_t b_q,
+                           uint64_t b_s, uint32_t b_rows_per_rec, uint64_t b_rec_stride, uint64_t c, uint32_t M, uint32_t N, uint32_t K,
+                           uint64_t out_dev) {
+  if (!M || !N || !K || (K % 32) || (K % 16)) return -22;
+  if ((a_q | b_q) & 15 || (c & 1)) return -22;
+  if (!a_rows_per_rec) a_rows_per_rec = M;
+  if (!b_rows_per_rec) b_rows_per_rec = N;
+  if ((a_rows_per_rec < M && a_rows_per_rec % BM) || (b_rows_per_rec < N && b_rows_per_rec % BN)) return -22;   // tiles must not straddle records
+  if ((a_rows_per_rec < M && (a_rec_stride % 16 || a_rec_stride < (uint64_t)a_rows_per_rec * K)) ||
+      (b_rows_per_rec < N && (b_rec_stride % 16 || b_rec_stride < (uint64_t)b_rows_per_rec * K))) return -22;
+  if (a_rows_per_rec >= M) a_rec_stride = (uint64_t)M * K;
+  if (b_rows_per_rec >= N) b_rec_stride = (uint64_t)N * K;
+  CUtensorMap ma, mb;
+  int rc = make_map3(&ma, (const void*)a_q, M, K, a_rows_per_rec, a_rec_stride >= 16 ? (a_rec_stride + 15) / 16 * 16 : 16);
+  if (!rc) rc = make_map3(&mb, (const void*)b_q, N, K, b_rows_per_rec, b_rec_stride >= 16 ? (b_rec_stride + 15) / 16 * 16 : 16);
+  if (rc) return rc;
+  MxArgs g;
+  g.a_s = (const uint8_t*)a_s; g.b_s = (const uint8_t*)b_s;
+  g.a_rec_stride = a_rec_stride; g.b_rec_stride = b_rec_stride; g.a_rows_per_rec = a_rows_per_rec; g.b_rows_per_rec = b_rows_per_rec;
+  g.c = (__nv_bfloat16*)c; g.M = M; g.N = N; g.K = K;
+  g.out = (unsigned long long*)out_dev;
+  unsigned long long* o = (unsigned long long*)out_dev;
+  for (int i = 0; i < 8; ++i) o[i] = 0;
+  const uint32_t n_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  if (grid <= 0) grid = 148;
+  if ((uint32_t)grid > n_tiles) grid = (int)n_tiles;
+  const size_t smem = sizeof(Smem) + 1024;
+  cudaError_t e = cudaFuncSetAttribute(gemm_mxfp8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return -(int)e - 1000;
+  gemm_mxfp8_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ma, mb, g);
+  return (int)cudaGetLastError();
+}
+
+extern "C" __attribute__((visibility("default"))) void rn_preload_gemm_mx() {
+  cudaFuncAttributes at;
+  cudaFuncGetAttributes(&at, gemm_mxfp8_kernel);
+  cudaFuncSetAttribute(gemm_mxfp8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Smem) + 1024));
+  encode_tiled();
+}

@@ -41,7 +41,7 @@ constexpr int kEpiThreads = 128;
 constexpr uint32_t kTmemCols = 512;                                // two 256-column accumulators
 constexpr unsigned long long kWaitNs = 2000000000ull;
 constexpr int kStageC = 32 * 128;                                  // one TMA-store box: 32 rows x 64 bf16, SWIZZLE_128B
-constexpr uint32_t kFlagDirect = 1, kFlagPlainStores = 2, kFlagDenseProbe = 4;
+constexpr uint32_t kFlagDirect = 1, kFlagPlainStores = 2, kFlagDenseProbe = 4, kFlagNoStreamK = 8;
 
 struct alignas(1024) Smem {
   uint8_t a[STAGES][A_STAGE];
@@ -69,6 +69,9 @@ struct GemmArgs {
                              //    each finished panel is announced by a zero-length RDMA_WRITE_IMM posted after a cumulative
                              //    system-scope fence (data plane = SM stores over NVLink, control plane = the RDMA queue pair)
   uint32_t group_m;          // tile rasterisation: this many M blocks advance together across N (L2 reuse of B)
+  float* ws;                 // stream-K workspace: per cluster boundary, 2 CTAs x 2 halves x 128 x 256 fp32 partial accumulators
+  unsigned int* ws_flags;    // [boundary][rank]: == epoch once that CTA's partial is complete
+  uint32_t epoch;            // launch stamp (never 0): flags need no reset between launches
   unsigned int* counters;    // [0..m_blks): tiles done per panel ; [m_blks]: CTAs done
   unsigned long long* acc;   // [0] max idx+1, [1] posted, [2] ~first post time
   unsigned long long* out;   // [status, t_start, t_end, posted, t_first_post, t_compute_end, 0, 0]
@@ -179,7 +182,8 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void epilogue_rows_tma(uint8_t (*stage)[kStageC], const CUtensorMap* mc, uint32_t taddr, int col0, int row0, int lane,
-                                                  uint32_t dense_n = 0) {
+                                                  uint32_t dense_n = 0, const float* addend_row = nullptr, uint32_t n_addends = 0,
+                                                  uint64_t addend_stride = 0) {
 #pragma unroll 1
   for (int c = 0; c < BN / 64; ++c) {
     const uint32_t buf = s32(stage[c & 1]);
@@ -189,6 +193,17 @@ __device__ __forceinline__ void epilogue_rows_tma(uint8_t (*stage)[kStageC], con
     tmem_ld32(taddr + c * 64, r);
     tmem_ld32(taddr + c * 64 + 32, r + 32);
     tmem_ld_wait();
+    for (uint32_t i = 0; i < n_addends; ++i) {         // stream-K: the other clusters' shares of K for this row (fp32, 256 B per chunk)
+      const float4* p = reinterpret_cast<const float4*>(addend_row + (uint64_t)i * addend_stride) + (uint64_t)c * 16 * BM;   // [chunk*8 + j][row]
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float4 v = __ldcg(p + (uint64_t)j * BM);
+        r[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) + v.x);
+        r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + v.y);
+        r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + v.z);
+        r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + v.w);
+      }
+    }
     const uint32_t rowp = buf + lane * 128;
 #pragma unroll
     for (int j = 0; j < 8; ++j)
@@ -716,6 +731,56 @@ gemm_send3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const unsigned long long t_start = globaltimer_ns();
   const uint32_t mq_blks = g.M / (4 * BM), n_blks = g.N / BN, k_blks = g.K / BK;
   const uint32_t n_tiles = mq_blks * n_blks, n_clusters = gridDim.x / 2, cluster_id = blockIdx.x / 2;
+  // Schedule.  Whole tiles go round robin (cluster c takes tiles c, c + n_clusters, ...): clusters that run at the
+  // same time sit on neighbouring tiles of the grouped rasterisation, which keeps the operands they share in L2 (an
+  // even split of the whole unit sequence was tried first and lost 25 %: it shifts every cluster's start by a
+  // fraction of a tile, so concurrent clusters end up waves apart).  What round robin leaves is the last, partial
+  // wave of R = n_tiles % n_clusters tiles, during which n_clusters - R cluster pairs idle: 13.5 % of the run at
+  // 4096^3.  Stream-K (g.ws != nullptr) splits exactly that wave: its R * k_blks (tile, k-block) units are dealt out
+  // evenly to ALL clusters.  A tail tile is then computed by a run of neighbouring clusters; the one that has its
+  // first k-blocks owns it and folds the others' fp32 partials (parked in the workspace) into its epilogue.  A
+  // cluster's share is shorter than a tile, so it holds at most the tail end of one tile (computed first, parked)
+  // and the head of the next (computed last, owned): nobody waits on work that has not started.
+  const uint32_t W = n_tiles / n_clusters, R = n_tiles % n_clusters;
+  const bool streamk = g.ws != nullptr && R != 0;
+  const uint64_t tail_units = (uint64_t)R * k_blks;
+  // clusters that take part in the tail: all of them, unless that would leave shares of under 4 k-blocks (each
+  // share costs its owner one more partial to fold in); never fewer than R (then nothing is split at all)
+  uint32_t n_tail = n_clusters;
+  if (tail_units / 4 < n_tail) n_tail = (uint32_t)(tail_units / 4);
+  if (n_tail < R) n_tail = R;
+  const bool in_tail = cluster_id < n_tail;
+  const uint64_t t_begin = in_tail ? tail_units * cluster_id / n_tail : 0, t_end = in_tail ? tail_units * (cluster_id + 1) / n_tail : 0;
+  struct Seg { uint32_t tile, kb0, kb1, j; };
+  struct Cursor { uint32_t wave; uint64_t ut; };
+  auto next_seg = [&](Cursor& cur, Seg& sg) -> bool {
+    if (cur.wave < W) {
+      sg.tile = cur.wave * n_clusters + cluster_id; sg.kb0 = 0; sg.kb1 = k_blks; sg.j = ~0u;
+      ++cur.wave;
+      return true;
+    }
+    if (!streamk) {
+      if (cur.wave != W || cluster_id >= R) return false;
+      sg.tile = W * n_clusters + cluster_id; sg.kb0 = 0; sg.kb1 = k_blks; sg.j = ~0u;
+      ++cur.wave;
+      return true;
+    }
+    if (cur.ut >= t_end) return false;
+    sg.j = (uint32_t)(cur.ut / k_blks);
+    sg.tile = W * n_clusters + sg.j;
+    sg.kb0 = (uint32_t)(cur.ut % k_blks);
+    const uint64_t left = t_end - cur.ut;
+    sg.kb1 = (uint32_t)((uint64_t)sg.kb0 + left < k_blks ? sg.kb0 + left : k_blks);
+    cur.ut += sg.kb1 - sg.kb0;
+    return true;
+  };
+  // cluster that holds tail unit x (largest c with tail_units * c / n_tail <= x)
+  auto cluster_of = [&](uint64_t x) -> uint32_t {
+    uint32_t c = (uint32_t)(x * n_tail / tail_units) + 1;
+    if (c > n_tail - 1) c = n_tail - 1;
+    while (tail_units * c / n_tail > x) --c;
+    return c;
+  };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES3; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
@@ -740,10 +805,12 @@ gemm_send3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // ===================== TMA producer (both CTAs: own 256 rows of A, own half of B)
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (uint32_t tile = cluster_id; tile < n_tiles && !s.abort; tile += n_clusters) {
+      Cursor cur = {0, t_begin};
+      Seg sg;
+      while (!s.abort && next_seg(cur, sg)) {
         uint32_t mq, n_blk;
-        tile_coords(tile, mq_blks, n_blks, g.group_m, &mq, &n_blk);
-        for (uint32_t kb = 0; kb < k_blks; ++kb) {
+        tile_coords(sg.tile, mq_blks, n_blks, g.group_m, &mq, &n_blk);
+        for (uint32_t kb = sg.kb0; kb < sg.kb1; ++kb) {
           if (!mbar_wait_t(s, &s.empty[stage], phase ^ 1)) goto producer3_done;
           const uint32_t lbar = mapa(s32(&s.full[stage]), 0);
           if (leader) mbar_expect_tx(&s.full[stage], 2 * (A3_STAGE + BH_STAGE));
@@ -759,21 +826,24 @@ gemm_send3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // ===================== MMA issuer (leader CTA only): two M=256 pair-MMAs per k16, one per accumulator half
     if (leader && lane == 0) {
       uint32_t stage = 0, phase = 0, tphase = 0;
-      for (uint32_t tile = cluster_id; tile < n_tiles && !s.abort; tile += n_clusters) {
-        for (uint32_t kb = 0; kb < k_blks; ++kb) {
+      Cursor cur = {0, t_begin};
+      Seg sg;
+      while (!s.abort && next_seg(cur, sg)) {
+        for (uint32_t kb = sg.kb0; kb < sg.kb1; ++kb) {
           if (!mbar_wait_t(s, &s.full[stage], phase)) goto mma3_done;
           tc_fence_after();
           const uint64_t db = smem_desc(s.b[stage]);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            if (kb == 0) {                                                     // this half has been drained by both CTAs' epilogues
+            if (kb == sg.kb0) {                                                // this half has been drained by both CTAs' epilogues
               if (!mbar_wait_t(s, &s.tempty[h], tphase ^ 1)) goto mma3_done;
               tc_fence_after();
             }
             const uint64_t da = smem_desc(s.a[stage] + h * A_STAGE);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)
-              umma_f16_2sm(tmem_base + (uint32_t)h * BN, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc2, (kb | (uint32_t)k) != 0);
+              umma_f16_2sm(tmem_base + (uint32_t)h * BN, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc2,
+                           (kb != sg.kb0) || k != 0);
           }
           tc_commit_2sm(&s.empty[stage]);
           if (++stage == STAGES3) { stage = 0; phase ^= 1; }
@@ -788,22 +858,76 @@ gemm_send3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // ===================== epilogue (both CTAs: their own 256 rows = two 128-row panels of the tile)
     const uint32_t q = warp & 3;
     uint32_t tphase = 0;
+    Cursor cur = {0, t_begin};
+    Seg sg;
     const bool sys = g.qp != nullptr && poster_sys(g.qp);
     uint32_t pending0 = ~0u, pending1 = ~0u;
-    for (uint32_t tile = cluster_id; tile < n_tiles; tile += n_clusters) {
+    constexpr uint64_t kWsPerCta = 2ull * BM * BN;                              // floats: two 128 x 256 halves
+    while (next_seg(cur, sg)) {
       uint32_t mq, n_blk;
-      tile_coords(tile, mq_blks, n_blks, g.group_m, &mq, &n_blk);
+      tile_coords(sg.tile, mq_blks, n_blks, g.group_m, &mq, &n_blk);
       if (!mbar_wait_t(s, &s.tfull, tphase)) break;
       tphase ^= 1;
       tc_fence_after();
+      const bool contributor = sg.kb0 != 0;                                    // not the head of its tile: park the partial, store nothing
+      const uint32_t row_in_panel = q * 32 + lane;
+      if (contributor) {
+        float* wsb = g.ws + ((uint64_t)cluster_id * 2 + rank) * kWsPerCta;     // one slot per contributing cluster
+#pragma unroll 1
+        for (uint32_t h = 0; h < 2; ++h) {
+          const uint32_t taddr = tmem_base + ((q * 32u) << 16) + h * BN;
+          // layout private to this kernel, chosen for the accesses: [half][32-column chunk][float4 j][row] -- the 32 rows
+          // of a warp are 512 contiguous bytes per store / load instruction
+          float4* dst = reinterpret_cast<float4*>(wsb) + (uint64_t)h * (BN / 4) * BM + row_in_panel;
+#pragma unroll 2
+          for (int c = 0; c < BN / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld32(taddr + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              __stcg(dst + (uint64_t)(c * 8 + j) * BM, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                                  __uint_as_float(r[4 * j + 3])));
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (leader) mbar_arrive(&s.tempty[h]);
+            else mbar_arrive_remote(mapa(s32(&s.tempty[h]), 0));
+          }
+        }
+        __threadfence();                                                       // my rows of the partial before the flag
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        if (threadIdx.x == 64)
+          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(g.ws_flags + (uint64_t)cluster_id * 2 + rank), "r"(g.epoch) : "memory");
+        continue;
+      }
+      // head of a split tail tile: the clusters after this one computed the rest of K at the same time
+      uint32_t n_contrib = 0;
+      if (sg.j != ~0u && sg.kb1 != k_blks) n_contrib = cluster_of((uint64_t)(sg.j + 1) * k_blks - 1) - cluster_id;
+      for (uint32_t i = 1; i <= n_contrib && !s.abort; ++i) {
+        const unsigned int* flag = g.ws_flags + (uint64_t)(cluster_id + i) * 2 + rank;
+        unsigned long long t0 = 0;
+        unsigned int v;
+        for (unsigned n = 0;; ++n) {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+          if (v == g.epoch || s.abort) break;
+          if ((n & 63) == 63) {
+            if (!t0) t0 = globaltimer_ns();
+            else if (globaltimer_ns() - t0 > kWaitNs) { s.abort = 1; break; }
+          }
+        }
+      }
+      const float* wsa = n_contrib ? g.ws + ((uint64_t)(cluster_id + 1) * 2 + rank) * kWsPerCta : nullptr;
 #pragma unroll 1
       for (uint32_t h = 0; h < 2; ++h) {
         const uint32_t m_blk = mq * 4 + rank * 2 + h;                          // 128-row panel index
         const uint32_t taddr = tmem_base + ((q * 32u) << 16) + h * BN;
+        const float* add_row = wsa ? wsa + ((uint64_t)h * (BN / 4) * BM + row_in_panel) * 4 : nullptr;   // float4 [chunk*8 + j][row], see the contributor
         if (!g.out_fp8) {
-          epilogue_rows_tma(s.stage_c[q], &tmap_c, taddr, (int)(n_blk * BN), (int)(m_blk * BM + q * 32), lane);
+          epilogue_rows_tma(s.stage_c[q], &tmap_c, taddr, (int)(n_blk * BN), (int)(m_blk * BM + q * 32), lane, 0u, add_row, n_contrib,
+                            2 * kWsPerCta);
         } else {
-          const uint32_t row_in_panel = q * 32 + lane;
           uint8_t* rec = reinterpret_cast<uint8_t*>(g.c) + (uint64_t)m_blk * panel_record_bytes(g.N);
           uint8_t* qrow = rec + (size_t)row_in_panel * g.N + (size_t)n_blk * BN;
           uint8_t* srow = rec + (size_t)BM * g.N + (size_t)row_in_panel * (g.N / 32) + (size_t)n_blk * (BN / 32);
@@ -812,6 +936,17 @@ gemm_send3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             uint32_t r[32];
             tmem_ld32(taddr + c * 32, r);
             tmem_ld_wait();
+            for (uint32_t i = 0; i < n_contrib; ++i) {
+              const float4* p = reinterpret_cast<const float4*>(add_row + (uint64_t)i * 2 * kWsPerCta) + (uint64_t)c * 8 * BM;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 v = __ldcg(p + (uint64_t)j * BM);
+                r[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) + v.x);
+                r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + v.y);
+                r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + v.z);
+                r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + v.w);
+              }
+            }
             quantize_block(r, reinterpret_cast<uint4*>(qrow + c * 32), srow + c);
           }
         }
@@ -914,6 +1049,15 @@ RN_API uint64_t rn_gemm_panel_record_bytes(uint32_t N) { return (uint64_t)BM * N
 RN_API uint32_t rn_gemm_tile(uint32_t* bm, uint32_t* bn, uint32_t* bk) { *bm = BM; *bn = BN; *bk = BK; return STAGES; }
 
 // counters_dev: >= (M/128 + 1) * 4 + 32 bytes of zeroed device scratch (self-cleaning), out_dev: 64 B mapped pinned.
+// Stream-K workspace of the wide kernel: one slot per cluster boundary (at most 73 on 148 SMs) of 2 CTAs x 2 x 128 x 256
+// fp32, followed by the flags.  Set per device by the context that owns the memory (hca_host.cu allocates it with the
+// HCA: an allocation at launch time would stall behind a resident engine kernel).
+namespace { constexpr uint32_t kWsSlots = 80; constexpr uint64_t kWsSlotFloats = 2ull * 2 * BM * BN; }
+static float* g_ws[16] = {};
+static uint32_t g_epoch = 1;
+RN_API uint64_t rn_gemm_workspace_bytes() { return kWsSlots * kWsSlotFloats * 4 + kWsSlots * 2 * 4 + 256; }
+RN_API void rn_gemm_set_workspace(int dev, uint64_t ptr) { if (dev >= 0 && dev < 16) g_ws[dev] = (float*)ptr; }
+
 RN_API int rn_k_gemm_send(uint64_t stream, int grid, uint64_t a, uint64_t b, uint64_t c, uint32_t M, uint32_t N, uint32_t K,
                           uint64_t qp_dev, uint64_t c_va, uint32_t lkey, uint64_t remote_va, uint32_t rkey,
                           uint32_t signal_every, uint32_t with_imm, uint32_t out_fp8, uint32_t cta_group, uint32_t group_m, uint32_t flags, uint64_t counters_dev,
@@ -927,6 +1071,7 @@ RN_API int rn_k_gemm_send(uint64_t stream, int grid, uint64_t a, uint64_t b, uin
                                           : make_map(&mc, (const void*)c, M, N, 32);           // only dereferenced by the bf16 TMA-store epilogue
   if (rc) return rc;
   GemmArgs g;
+  g.ws = nullptr; g.ws_flags = nullptr; g.epoch = 0;
   g.c = (__nv_bfloat16*)c; g.M = M; g.N = N; g.K = K; g.qp = (QpDev*)qp_dev; g.c_va = c_va; g.lkey = lkey; g.rkey = rkey;
   g.remote_va = remote_va; g.signal_every = signal_every ? signal_every : 1; g.with_imm = with_imm & 1u; g.post_only = (with_imm >> 1) & 1u; g.out_fp8 = out_fp8; g.group_m = group_m ? group_m : 1;
   g.direct = (flags & kFlagDirect) ? 1 : 0; g.plain_stores = (flags & kFlagPlainStores) ? 1 : 0; g.dense_probe = (flags & kFlagDenseProbe) ? 1 : 0;
@@ -949,6 +1094,19 @@ RN_API int rn_k_gemm_send(uint64_t stream, int grid, uint64_t a, uint64_t b, uin
     grid &= ~1;
     if ((uint32_t)grid > 2 * n_tiles) grid = (int)(2 * n_tiles);
     if (g.group_m > 1) g.group_m = (g.group_m + 1) / 2;              // group_m is given in 256-row units; tiles here are 512 rows
+    {
+      // stream-K needs every cluster resident at once (a tile's two halves are computed by neighbouring clusters):
+      // true for grid <= #SMs with one CTA per SM, which the caller controls; kFlagNoStreamK opts out
+      int dev = 0;
+      cudaGetDevice(&dev);
+      float* ws = (dev >= 0 && dev < 16) ? g_ws[dev] : nullptr;
+      // worth it only when whole tiles do not divide evenly among the clusters (round robin is then perfectly balanced)
+      const bool want = !(flags & kFlagNoStreamK) && ws && (uint32_t)(grid / 2) <= kWsSlots && n_tiles % (uint32_t)(grid / 2) != 0;
+      g.ws = want ? ws : nullptr;
+      g.ws_flags = want ? (unsigned int*)(ws + kWsSlots * kWsSlotFloats) : nullptr;
+      if (++g_epoch == 0) g_epoch = 1;
+      g.epoch = g_epoch;
+    }
     const size_t smem = sizeof(Smem3) + 1024;
     cudaError_t e = cudaFuncSetAttribute(gemm_send3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return -(int)e - 1000;

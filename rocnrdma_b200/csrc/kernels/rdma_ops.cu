@@ -84,7 +84,15 @@ __global__ void __launch_bounds__(32, 1) rdma_stream_kernel(StreamArgs a) {
         poster_build_rdma(p, idx + lane, (uint8_t)a.opcode, lbase + off, a.lkey, rbase + off, a.rkey, a.bytes, flags);
     }
     if (n > 1) __syncwarp();                         // the burst's WQE bytes happen-before lane 0's release
-    if (lane == 0) poster_ring(p, idx + n);
+    if (lane == 0) {
+      // overlap the completion poll with the doorbell release: the CQE load is in flight while the fence in
+      // front of the doorbell waits for the WQE stores (one exposed round trip per post instead of two)
+      const bool outstanding = p.head > p.cons;
+      uint4 tail = make_uint4(0, 0, 0, 0);
+      if (outstanding) tail = poster_peek(p);
+      poster_ring(p, idx + n);
+      if (outstanding && poster_take(p, tail) < 0) status = WAIT_CQE_ERROR;
+    }
     last = idx + n - 1;
     done += n;
   }

@@ -71,7 +71,7 @@ def dequant_fp8_panels(rec: torch.Tensor, M: int, Nn: int) -> torch.Tensor:
 
 
 def gemm_send(ctx, a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, c_mr=None, qp=None, dst_mr=None,
-              signal_every: int = 1, with_imm: bool = False, out_fp8: bool = False, cta_group: int = 0, group_m: int = 0, direct: bool = False, plain_stores: bool = False, grid: int = 0, timeout_ms: int = 2000, stream=None, sync: bool = True, post_only: bool = False,
+              signal_every: int = 1, with_imm: bool = False, out_fp8: bool = False, cta_group: int = 0, group_m: int = 0, direct: bool = False, plain_stores: bool = False, grid: int = 0, timeout_ms: int = 2000, stream=None, sync: bool = True, post_only: bool = False, stream_k: bool = False,
               scratch_slot: int = 2):
     """``c[M,N] = a[M,K] @ b[N,K].T`` (bf16 in/out, fp32 accumulate on the 5th-gen tensor cores).
 
@@ -85,7 +85,10 @@ def gemm_send(ctx, a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, c_mr=None,
     ``group_m``: M blocks that advance together across N (L2 reuse of B; 0 = 8 for compute only, 4 when sending).
     ``cta_group``: 3 = wide CTA-pair kernel (512x256 per pair, 256 rows of A per CTA, the shape cuBLAS's nvjet
     kernels use), 2 = CTA-pair kernel (256x256 per pair), 1 = single-CTA 128x256 kernel, 0 (default) = the widest
-    the shape allows (M % 512, M % 256).
+    the shape allows (M % 512 and K >= 4096, else M % 256).
+    ``stream_k`` (wide kernel only): split the tiles of the last, partial wave along K over all CTA pairs and fold the
+    fp32 partials back in the owner's epilogue.  Correct and tested, but a measured loss on this box (the partial write +
+    read-back and the serialised extra epilogue cost more than the idle pairs: -9 % at 4096^3), so it is off by default.
     """
     for t in (a, b):
         assert t.dtype == torch.bfloat16 and t.is_contiguous()
@@ -102,7 +105,10 @@ def gemm_send(ctx, a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, c_mr=None,
     if qp is not None and (c_mr is None or dst_mr is None):
         raise ValueError("sending needs c_mr (registration of c) and dst_mr")
     if cta_group == 0:
-        wide_ok = M % (4 * BM) == 0 and not direct and not plain_stores and not os.environ.get("RN_GEMM_DENSE_PROBE")
+        # measured against cuBLAS on the same box (profiles/README.md): the wide kernel moves a quarter less operand traffic
+        # and wins from K = 4096 up (0.97x cuBLAS at 8192^3 where the pair kernel is 0.93x); its TMEM is single-buffered, so
+        # with short K loops the exposed epilogue costs more than the traffic saves and the double-buffered pair kernel wins
+        wide_ok = M % (4 * BM) == 0 and K >= 4096 and not direct and not plain_stores and not os.environ.get("RN_GEMM_DENSE_PROBE")
         cta_group = 3 if wide_ok else (2 if M % (2 * BM) == 0 else 1)
     if os.environ.get("RN_GEMM_CTA_GROUP"):            # A/B switch for benchmarks
         cta_group = int(os.environ["RN_GEMM_CTA_GROUP"])
@@ -118,7 +124,7 @@ def gemm_send(ctx, a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, c_mr=None,
     rc = lib.rn_k_gemm_send(_stream_ptr(ws), grid, a.data_ptr(), b.data_ptr(), c.data_ptr(), M, Nn, K,
                             qp.dev_ptr if qp is not None else 0, c_mr.addr if c_mr is not None else 0,
                             c_mr.lkey if c_mr is not None else 0, dst_mr.addr if dst_mr is not None else 0,
-                            dst_mr.rkey if dst_mr is not None else 0, signal_every, int(with_imm) | (2 if post_only else 0), int(out_fp8), cta_group, group_m, int(direct) | (2 if plain_stores else 0) | (4 if os.environ.get("RN_GEMM_DENSE_PROBE") else 0), counters, out_addr, timeout_ms)
+                            dst_mr.rkey if dst_mr is not None else 0, signal_every, int(with_imm) | (2 if post_only else 0), int(out_fp8), cta_group, group_m, int(direct) | (2 if plain_stores else 0) | (4 if os.environ.get("RN_GEMM_DENSE_PROBE") else 0) | (8 if (not stream_k or os.environ.get("RN_GEMM_NO_STREAMK")) else 0), counters, out_addr, timeout_ms)
     if rc:
         raise N.NativeError(f"gemm_send launch failed ({rc})")
     if not sync:

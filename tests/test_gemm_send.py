@@ -221,3 +221,41 @@ def test_gemm_wide_send_panels(ctx, out_fp8):
         assert torch.equal(d, ops.gemm.ref_fp8_panels(ref)) or torch.allclose(ops.gemm.dequant_fp8_panels(d, M, N), ref, rtol=0.08, atol=0.5)
     else:
         assert torch.allclose(d.float(), ref, rtol=2e-2, atol=0.5)
+
+
+@pytest.mark.parametrize("M,N,K,grid", [(1024, 1024, 512, 6), (1536, 768, 1024, 10), (2560, 2048, 2048, 60), (512, 768, 4096, 4), (4096, 4096, 1024, 148)])
+def test_gemm_wide_stream_k_matches_fp32_reference(ctx, M, N, K, grid):
+    """Tiles do not divide evenly among the clusters: some are split along K between neighbouring clusters and folded
+    back together through the fp32 workspace.  Same answer as the unsplit schedule, bit for bit is not required
+    (different summation order), fp32-reference accuracy is."""
+    a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    b = torch.randn(N, K, device="cuda").to(torch.bfloat16)
+    c = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    c2 = torch.zeros_like(c)
+    n_tiles = (M // 512) * (N // 256)
+    assert n_tiles % min(grid // 2, n_tiles) != 0, "pick a grid that leaves a partial wave"
+    for _ in range(2):                                               # twice: the epoch-stamped flags need no reset
+        r = ops.gemm_send(ctx, a, b, c, cta_group=3, grid=grid, stream_k=True)
+        assert r.ok, r.status
+    assert ops.gemm_send(ctx, a, b, c2, cta_group=3, grid=grid, stream_k=False).ok
+    ref = a.float() @ b.float().T
+    tol = 0.5 * (K / 256) ** 0.5
+    assert torch.allclose(c.float(), ref, rtol=2e-2, atol=tol)
+    assert torch.allclose(c.float(), c2.float(), rtol=2e-2, atol=tol)
+
+
+def test_gemm_wide_stream_k_send_and_fp8(ctx):
+    M, N, K = 1024, 768, 1024                                        # 6 tiles over 4 clusters
+    a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    b = torch.randn(N, K, device="cuda").to(torch.bfloat16)
+    nb = (M // 128) * ops.gemm.panel_record_bytes(N)
+    c = torch.zeros(nb, dtype=torch.uint8, device="cuda")
+    d = torch.zeros_like(c)
+    cm, dm = ctx.reg_mr(c), ctx.reg_mr(d)
+    qp = ctx.loopback_qp(depth=64)
+    ctx.engine_start(ctas=8, idle_timeout_ms=3000)
+    r = ops.gemm_send(ctx, a, b, c, c_mr=cm, qp=qp, dst_mr=dm, cta_group=3, out_fp8=True, grid=8, stream_k=True)
+    ctx.engine_stop()
+    assert r.ok and r.panels_posted == M // 128 and torch.equal(c, d)
+    ref = a.float() @ b.float().T
+    assert torch.allclose(ops.gemm.dequant_fp8_panels(d, M, N), ref, rtol=0.08, atol=1.0)
