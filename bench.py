@@ -28,14 +28,33 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Library banners (NCCL prints its version to stdout under NCCL_DEBUG=VERSION) must not share stdout with the
+    result: point fd 1 at stderr for the run and keep the original for the one JSON line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def reference_arm():
     # `pip install --no-index ... /root/reference` fails: the reference is a Linux kernel module for
     # AMD KFD + MLNX_OFED 3.2 (no setup.py / pyproject, no userspace, needs amd_rdma.h); see DESIGN.md.
     if int(os.environ.get("RANK", "0")) != 0:      # launched like our own arm (torchrun for N > 1): one line, from rank 0
         return 0
-    print(json.dumps({"impl": "reference",
-                      "unavailable": "reference is an AMD-KFD/MLNX_OFED kernel module (amdp2p.ko): not pip-installable, "
-                                     "no userspace entry point, cannot build or load on a B200 box"}))
+    emit({"impl": "reference",
+          "unavailable": "reference is an AMD-KFD/MLNX_OFED kernel module (amdp2p.ko): not pip-installable, "
+                         "no userspace entry point, cannot build or load on a B200 box"})
     return 0
 
 
@@ -55,6 +74,7 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm()
+    quiet_stdout()
 
     import torch
     import rocnrdma_b200 as rn
@@ -73,8 +93,8 @@ def main():
     if not torch.cuda.is_available():
         # the GPU-initiated path has no CPU fallback by design: say so in one line instead of a traceback
         if rank == 0:
-            print(json.dumps({"metric": "rdma_write_gbps_gpu_hbm_device_timed", "value": None, "impl": "ours",
-                              "unavailable": "no CUDA device visible: the data path is sm_100a kernels only"}))
+            emit({"metric": "rdma_write_gbps_gpu_hbm_device_timed", "value": None, "impl": "ours",
+                  "unavailable": "no CUDA device visible: the data path is sm_100a kernels only"})
         return 2
     torch.cuda.set_device(local_rank)
     from rocnrdma_b200.utils.affinity import bind_to_gpu
@@ -365,7 +385,25 @@ def main():
                 row = extras.setdefault("gemm_send", {}).setdefault(f"{M}x{Nn}x{K}", {})
                 row.update({"cublas_tflops": round(cublas, 1), "ours_tflops": round(ours, 1), "ours_best_single_launch_tflops": round(best, 1),
                             "vs_cublas": round(ours / cublas, 3), "frac_of_sustained_peak": round(ours / sustained, 3) if sustained else None,
+                            "kernel": "wide pair (512x256 per CTA pair)" if K >= 4096 and M % 512 == 0 else "pair (256x256 per CTA pair)",
                             "timing": "10 back-to-back launches between CUDA events, both libraries", "numerics_ok": good})
+                # K7: the same product with block-scaled fp8 operands (what a receiver of K3 / K4 records multiplies)
+                from rocnrdma_b200.ops import gemm_mx as MX
+                (aq, as_), (bq, bs) = MX.quantize_mx(a), MX.quantize_mx(b)
+                oa, ob = MX.MxOperand.from_tensors(aq, as_), MX.MxOperand.from_tensors(bq, bs)
+                for _ in range(2):
+                    ops.gemm_mxfp8(ctx, oa, ob, c)
+                with torch.cuda.stream(stream):
+                    ev[2].record()
+                    for _ in range(10):
+                        ops.gemm_mxfp8(ctx, oa, ob, c, sync=False, stream=stream)
+                    ev[3].record()
+                ev[3].synchronize()
+                mx = flops * 10 / (ev[2].elapsed_time(ev[3]) * 1e-3) / 1e12
+                refq = MX.dequantize_mx(aq[:128], as_[:128]) @ MX.dequantize_mx(bq, bs).T
+                row.update({"mxfp8_block_scaled_tflops": round(mx, 1),
+                            "mxfp8_numerics_ok": bool((c[:128].float() - refq).abs().max().item() <= 2e-2 * refq.abs().max().item() + 1e-3)})
+                del aq, as_, bq, bs
         except Exception as e:
             extras.setdefault("gemm_send", {})["compute_only_error"] = str(e)[:200]
     if softhca:
@@ -439,7 +477,7 @@ def main():
                                                    "error_cqes": counters["n_err"], "doorbell_order_violations": counters["n_db_order_violations"]},
             "extras": extras,
         }
-        print(json.dumps(out))
+        emit(out)
     if dist is not None:
         dist.destroy_process_group()
     ctx.close()
