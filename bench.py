@@ -418,6 +418,31 @@ def main():
             except Exception as e:
                 extras["engine_128_ctas"] = {"error": str(e)[:160]}
     torch.cuda.synchronize()
+    if args.extras and world > 1 and softhca:
+        # BASELINE config 4 at N >= 2: GEMM on GPU0, every finished panel lands in GPU1's HBM over NVLink, consumer kernel
+        # on GPU1 polls the receive CQ.  One process drives both GPUs (two HCA contexts, QP to QP), so rank 0 runs it while
+        # the other ranks wait on the host (a NCCL barrier would put a spinning kernel of another process on GPU1).
+        store = torch.distributed.distributed_c10d._get_default_store()
+        if rank == 0:
+            try:
+                from rocnrdma_b200.models import sendrecv_gemm as SG
+                res = {}
+                for shape, mode in (((8192, 8192, 2048), "engine"), ((4096, 4096, 4096), "direct")):
+                    r4 = SG.run(*shape, mode=mode, gpus=(local_rank, local_rank + 1), reps=3)
+                    res["x".join(str(v) for v in shape)] = {
+                        "mode": r4.mode, "ok": bool(r4.ok and r4.verified), "fused_gemm_send_recv_us": round(r4.fused_us, 1),
+                        "gemm_then_write_us": round(r4.unfused_us, 1), "fused_speedup": round(r4.unfused_us / r4.fused_us, 3),
+                        "tflops_incl_delivery": round(r4.tflops, 1), "wire_gbps": round(r4.wire_gbps, 1), "panels": r4.panels,
+                        "engine_ctas": r4.engine_ctas,
+                        "limiter": ("NVLink store burstiness: all GEMM CTAs reach their epilogue together (~450 GB/s of SM-issued stores)"
+                                    if r4.mode == "direct" else "the 32 SMs the engine takes from the GEMM")}
+                extras["config4_gemm_send_recv_nvlink"] = res
+            except Exception as e:
+                extras["config4_gemm_send_recv_nvlink"] = {"error": str(e)[:200]}
+            finally:
+                store.set("rn_cfg4_done", "1")
+        else:
+            store.wait(["rn_cfg4_done"])
     if args.extras and rank == 0 and softhca:
         try:   # the ConnectX code path, executed: same kernels, verbs wire, the in-tree mock provider as the NIC
             extras["verbs_wire_mock_nic"] = mock_nic_extra(rn, ops, W, N, C, local_rank, src, dst)

@@ -25,6 +25,7 @@ class GemmResult:
     M: int
     N: int
     K: int
+    issuer_cycles: dict | None = None
 
     @property
     def ok(self) -> bool:
@@ -51,8 +52,11 @@ def panel_record_bytes(N: int) -> int:
 def ref_fp8_panels(c_fp32: torch.Tensor) -> torch.Tensor:
     """PyTorch reference of the fp8 epilogue: quantise an fp32 [M, N] result into panel records."""
     from .pack import _pow2, _scale_exponent
-    M, Nn = c_fp32.shape
-    x = c_fp32.float().reshape(M, Nn // 32, 32)
+    M0, Nn = c_fp32.shape
+    M = -(-M0 // BM) * BM                    # records are whole panels: rows past M quantise zeros
+    x = torch.zeros(M, Nn, dtype=torch.float32, device=c_fp32.device)
+    x[:M0] = c_fp32.float()
+    x = x.reshape(M, Nn // 32, 32)
     e = _scale_exponent(x.abs().amax(dim=2))
     q = (x * _pow2(-e)[..., None]).to(torch.float8_e4m3fn).view(torch.uint8).reshape(M, Nn)
     sc = (e + 127).to(torch.uint8)
@@ -64,10 +68,11 @@ def ref_fp8_panels(c_fp32: torch.Tensor) -> torch.Tensor:
 
 def dequant_fp8_panels(rec: torch.Tensor, M: int, Nn: int) -> torch.Tensor:
     from .pack import _pow2
-    r = rec.reshape(M // BM, panel_record_bytes(Nn))
-    q = r[:, :BM * Nn].contiguous().view(torch.float8_e4m3fn).float().reshape(M, Nn // 32, 32)
-    e = r[:, BM * Nn:].to(torch.int32).reshape(M, Nn // 32) - 127
-    return (q * _pow2(e)[..., None]).reshape(M, Nn)
+    P = -(-M // BM)
+    r = rec[:P * panel_record_bytes(Nn)].reshape(P, panel_record_bytes(Nn))
+    q = r[:, :BM * Nn].contiguous().view(torch.float8_e4m3fn).float().reshape(P * BM, Nn // 32, 32)
+    e = r[:, BM * Nn:].to(torch.int32).reshape(P * BM, Nn // 32) - 127
+    return (q * _pow2(e)[..., None]).reshape(P * BM, Nn)[:M]
 
 
 def gemm_send(ctx, a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, c_mr=None, qp=None, dst_mr=None,
@@ -77,7 +82,9 @@ def gemm_send(ctx, a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, c_mr=None,
 
     With ``qp``/``c_mr``/``dst_mr`` every finished 128-row panel of ``c`` is RDMA-written to the same
     offset of ``dst_mr`` from inside the kernel; the call returns when the last panel has landed.
-    Shapes must be multiples of the tile: M % 128 == 0, N % 256 == 0, K % 64 == 0.
+    Shapes: any M; N % 8 == 0 and K % 8 == 0 (16-byte rows for TMA), N % 32 == 0 for fp8 output.  Tiles that hang over an
+    edge are zero-filled on load and clipped on store by TMA; the last panel sent may be short.  ``direct`` and
+    ``plain_stores`` keep the tile-multiple restriction (M % 128, N % 256, K % 64).
     ``direct``: ``c`` is itself the peer's registered buffer (a tensor on the other GPU): the epilogue stores
     rows over NVLink and each panel is announced by a zero-length RDMA_WRITE_IMM (needs ``qp``, ``c_mr`` = the
     peer region as seen locally, ``dst_mr``).
@@ -96,12 +103,14 @@ def gemm_send(ctx, a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, c_mr=None,
     Nn, K2 = b.shape
     assert K == K2 and c.is_contiguous()
     if out_fp8:
-        # c is a uint8 buffer of M/128 panel records (block-scaled e4m3 + UE8M0 scales)
-        assert c.dtype == torch.uint8 and c.numel() >= (M // BM) * panel_record_bytes(Nn)
+        # c is a uint8 buffer of ceil(M/128) panel records (block-scaled e4m3 + UE8M0 scales)
+        assert c.dtype == torch.uint8 and c.numel() >= -(-M // BM) * panel_record_bytes(Nn)
     else:
         assert c.dtype == torch.bfloat16 and tuple(c.shape) == (M, Nn)
-    if M % BM or Nn % BN or K % BK:
-        raise ValueError(f"shape ({M},{Nn},{K}) must be a multiple of the ({BM},{BN},{BK}) tile")
+    if Nn % 8 or K % 8 or (out_fp8 and Nn % 32):
+        raise ValueError(f"shape ({M},{Nn},{K}): N and K must be multiples of 8 (16-byte rows), N of 32 for fp8 output")
+    if (direct or plain_stores) and (M % BM or Nn % BN or K % BK):
+        raise ValueError(f"direct / plain_stores need multiples of the ({BM},{BN},{BK}) tile, got ({M},{Nn},{K})")
     if qp is not None and (c_mr is None or dst_mr is None):
         raise ValueError("sending needs c_mr (registration of c) and dst_mr")
     if cta_group == 0:
@@ -118,7 +127,7 @@ def gemm_send(ctx, a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, c_mr=None,
         group_m = 8 if qp is None else 4
     lib = N.load()
     ws = work_stream(ctx, stream)
-    m_blks = M // BM
+    m_blks = -(-M // BM)
     counters = ctx.dev_scratch((m_blks + 1) * 4 + 64, offset=scratch_slot * (256 << 10))
     out_addr, out_view = ctx.scratch(64, offset=4096 + scratch_slot * 64)
     rc = lib.rn_k_gemm_send(_stream_ptr(ws), grid, a.data_ptr(), b.data_ptr(), c.data_ptr(), M, Nn, K,
@@ -135,4 +144,8 @@ def gemm_send(ctx, a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, c_mr=None,
 
 def parse(view, M, Nn, K) -> GemmResult:
     w = (C.c_int64 * 8).from_buffer(view)
-    return GemmResult(WAIT_STATUS.get(w[0], str(w[0])), w[1], w[2], w[3], w[4], w[5], M, Nn, K)
+    r = GemmResult(WAIT_STATUS.get(w[0], str(w[0])), w[1], w[2], w[3], w[4], w[5], M, Nn, K)
+    # wide kernel only: the MMA issuer of cluster 0 reports (cycles waiting for operands, for TMEM, in its loop)
+    u = w[7] & 0xFFFFFFFFFFFFFFFF
+    r.issuer_cycles = {"wait_operands": (u & 0x1FFFFF) << 4, "wait_tmem": ((u >> 21) & 0x1FFFFF) << 4, "loop": (u >> 42) << 4} if u else None
+    return r

@@ -65,11 +65,86 @@ def test_gemm_send_panels_arrive_and_match(ctx):
 
 
 def test_gemm_rejects_bad_shapes(ctx):
-    a = torch.zeros(100, 64, device="cuda:0", dtype=torch.bfloat16)
-    b = torch.zeros(256, 64, device="cuda:0", dtype=torch.bfloat16)
+    # rows must be 16-byte multiples for TMA: N % 8, K % 8 (N % 32 for fp8 records); the measurement switches keep the tile rule
+    a = torch.zeros(100, 68, device="cuda:0", dtype=torch.bfloat16)
+    b = torch.zeros(256, 68, device="cuda:0", dtype=torch.bfloat16)
     c = torch.zeros(100, 256, device="cuda:0", dtype=torch.bfloat16)
     with pytest.raises(ValueError):
         ops.gemm_send(ctx, a, b, c)
+    a = torch.zeros(100, 64, device="cuda:0", dtype=torch.bfloat16)
+    b = torch.zeros(260, 64, device="cuda:0", dtype=torch.bfloat16)
+    with pytest.raises(ValueError):
+        ops.gemm_send(ctx, a, b, torch.zeros(100, 260, device="cuda:0", dtype=torch.bfloat16))
+    b = torch.zeros(256, 64, device="cuda:0", dtype=torch.bfloat16)
+    with pytest.raises(ValueError):
+        ops.gemm_send(ctx, a, b, c, plain_stores=True)
+
+
+RAGGED = [(100, 256, 64), (1000, 520, 328), (130, 8, 8), (384, 264, 72), (515, 1000, 4104), (257, 1032, 200)]
+
+
+@pytest.mark.parametrize("cta_group", [1, 2, 3])
+@pytest.mark.parametrize("M,N,K", RAGGED)
+def test_gemm_ragged_shapes_match_fp32_reference(ctx, M, N, K, cta_group):
+    """No tile multiples anywhere: TMA zero-fills the loads that hang over an edge and clips the stores.  Guard rows /
+    columns around C prove nothing is written outside it."""
+    torch.manual_seed(M * 7 + N * 3 + K + cta_group)
+    a = torch.randn(M, K, device="cuda:0").to(torch.bfloat16)
+    b = torch.randn(N, K, device="cuda:0").to(torch.bfloat16)
+    buf = torch.full(((M + 2) * N + 64,), 7.0, device="cuda:0", dtype=torch.bfloat16)
+    off = N + 8                                     # keeps the 16-byte alignment TMA needs
+    c = buf[off:off + M * N].view(M, N)
+    torch.cuda.synchronize()
+    r = ops.gemm_send(ctx, a, b, c, cta_group=cta_group)
+    assert r.ok, r.status
+    _check(c, _ref(a, b), K)
+    assert torch.all(buf[:off] == 7.0) and torch.all(buf[off + M * N:] == 7.0), "stored outside C"
+
+
+@pytest.mark.parametrize("cta_group", [1, 2, 3])
+def test_gemm_ragged_send_short_last_panel(ctx, cta_group):
+    """M = 3 panels and 40 rows: four RDMA writes, the last one 40 rows long, nothing beyond it at the destination."""
+    M, N, K = 424, 520, 200
+    torch.manual_seed(5 + cta_group)
+    a = torch.randn(M, K, device="cuda:0").to(torch.bfloat16)
+    b = torch.randn(N, K, device="cuda:0").to(torch.bfloat16)
+    c = torch.zeros(M, N, device="cuda:0", dtype=torch.bfloat16)
+    d = torch.full((M + 16, N), 3.0, device="cuda:0", dtype=torch.bfloat16)
+    cm, dm = ctx.reg_mr(c), ctx.reg_mr(d)
+    qp = ctx.loopback_qp(depth=64)
+    torch.cuda.synchronize()
+    ctx.engine_start(ctas=16, idle_timeout_ms=3000)
+    try:
+        r = ops.gemm_send(ctx, a, b, c, c_mr=cm, qp=qp, dst_mr=dm, cta_group=cta_group, grid=16)
+    finally:
+        ctx.engine_stop()
+    assert r.ok and r.panels_posted == 4, r
+    _check(c, _ref(a, b), K)
+    assert torch.equal(d[:M], c) and torch.all(d[M:] == 3.0)
+
+
+@pytest.mark.parametrize("cta_group", [1, 2, 3])
+@pytest.mark.parametrize("M,N,K", [(300, 288, 200), (128, 32, 64), (700, 1056, 520)])
+def test_gemm_ragged_fp8_records(ctx, M, N, K, cta_group):
+    """fp8 epilogue through the staged TMA store at shapes that clip: whole records for ceil(M / 128) panels, columns
+    beyond N never written (the byte after the last record stays untouched)."""
+    torch.manual_seed(M + N + K + cta_group)
+    a = torch.randn(M, K, device="cuda:0").to(torch.bfloat16)
+    b = torch.randn(N, K, device="cuda:0").to(torch.bfloat16)
+    P = -(-M // 128)
+    nb = P * ops.panel_record_bytes(N)
+    c = torch.full((nb + 256,), 0xAB, dtype=torch.uint8, device="cuda:0")
+    torch.cuda.synchronize()
+    r = ops.gemm_send(ctx, a, b, c, out_fp8=True, cta_group=cta_group)
+    assert r.ok, r.status
+    assert torch.all(c[nb:] == 0xAB), "stored beyond the last record"
+    ref32 = _ref(a, b)
+    ref_rec = ops.ref_fp8_panels(ref32)
+    mism = (c[:nb] != ref_rec).float().mean().item()
+    assert mism < 0.02, f"{mism:.4f} of the record bytes differ from the reference quantisation"
+    got = ops.dequant_fp8_panels(c[:nb], M, N)
+    blk = ref32.reshape(M, N // 32, 32).abs().amax(dim=2, keepdim=True).expand(-1, -1, 32).reshape(M, N)
+    assert torch.all((got - ref32).abs() <= blk * (2.0 ** -4) * 1.05 + 1e-2)
 
 
 def test_gemm_fp8_epilogue_records_match_reference_and_arrive(ctx):
