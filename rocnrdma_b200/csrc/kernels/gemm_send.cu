@@ -409,13 +409,15 @@ __device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t da, uint6
                "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Bounded wait of one thread (producer, MMA issuer); false = timed out or another role aborted.  The retry sleeps in the
+// hardware (suspend-time hint) instead of spinning: ncu counted 4.4x the library's instructions for the spinning version.
 template <typename S>
 __device__ __forceinline__ bool mbar_wait_t(S& s, uint64_t* b, uint32_t parity) {
   if (mbar_try(b, parity)) return true;
   unsigned long long t0 = globaltimer_ns();
   unsigned n = 0;
-  while (!mbar_try(b, parity)) {
-    if ((++n & 255) == 0) {
+  while (!mbar_try_hint(b, parity, 10000u)) {
+    if ((++n & 7) == 0) {
       if (s.abort) return false;
       if (globaltimer_ns() - t0 > kWaitNs) { s.abort = 1; return false; }
     }

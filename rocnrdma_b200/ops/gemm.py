@@ -26,6 +26,7 @@ class GemmResult:
     N: int
     K: int
     issuer_cycles: dict | None = None
+    variant: int = 0          # kernel that ran: 1 = single CTA, 2 = CTA pair, 3 = wide CTA pair
 
     @property
     def ok(self) -> bool:
@@ -92,7 +93,7 @@ def gemm_send(ctx, a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, c_mr=None,
     ``group_m``: M blocks that advance together across N (L2 reuse of B; 0 = 8 for compute only, 4 when sending).
     ``cta_group``: 3 = wide CTA-pair kernel (512x256 per pair, 256 rows of A per CTA, the shape cuBLAS's nvjet
     kernels use), 2 = CTA-pair kernel (256x256 per pair), 1 = single-CTA 128x256 kernel, 0 (default) = the widest
-    the shape allows (M % 512 and K >= 4096, else M % 256).
+    the shape allows (M % 512 and K >= 6144, else M % 256).
     ``stream_k`` (wide kernel only): split the tiles of the last, partial wave along K over all CTA pairs and fold the
     fp32 partials back in the owner's epilogue.  Correct and tested, but a measured loss on this box (the partial write +
     read-back and the serialised extra epilogue cost more than the idle pairs: -9 % at 4096^3), so it is off by default.
@@ -115,9 +116,10 @@ def gemm_send(ctx, a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, c_mr=None,
         raise ValueError("sending needs c_mr (registration of c) and dst_mr")
     if cta_group == 0:
         # measured against cuBLAS on the same box (profiles/README.md): the wide kernel moves a quarter less operand traffic
-        # and wins from K = 4096 up (0.97x cuBLAS at 8192^3 where the pair kernel is 0.93x); its TMEM is single-buffered, so
-        # with short K loops the exposed epilogue costs more than the traffic saves and the double-buffered pair kernel wins
-        wide_ok = M % (4 * BM) == 0 and K >= 4096 and not direct and not plain_stores and not os.environ.get("RN_GEMM_DENSE_PROBE")
+        # and wins at K = 8192 (0.96-0.97x cuBLAS at 8192^3 where the pair kernel is 0.92-0.93x); its TMEM is single-buffered
+        # and reading an accumulator half out of TMEM takes ~1.5 k cycles whatever the number of epilogue warps, so with
+        # shorter K loops (4096^3: 0.91-0.96 vs 0.95-0.97) the double-buffered pair kernel is the better choice
+        wide_ok = M % (4 * BM) == 0 and K >= 6144 and not direct and not plain_stores and not os.environ.get("RN_GEMM_DENSE_PROBE")
         cta_group = 3 if wide_ok else (2 if M % (2 * BM) == 0 else 1)
     if os.environ.get("RN_GEMM_CTA_GROUP"):            # A/B switch for benchmarks
         cta_group = int(os.environ["RN_GEMM_CTA_GROUP"])
@@ -146,6 +148,7 @@ def parse(view, M, Nn, K) -> GemmResult:
     w = (C.c_int64 * 8).from_buffer(view)
     r = GemmResult(WAIT_STATUS.get(w[0], str(w[0])), w[1], w[2], w[3], w[4], w[5], M, Nn, K)
     # wide kernel only: the MMA issuer of cluster 0 reports (cycles waiting for operands, for TMEM, in its loop)
+    r.variant = int(w[6])
     u = w[7] & 0xFFFFFFFFFFFFFFFF
     r.issuer_cycles = {"wait_operands": (u & 0x1FFFFF) << 4, "wait_tmem": ((u >> 21) & 0x1FFFFF) << 4, "loop": (u >> 42) << 4} if u else None
     return r
