@@ -922,6 +922,11 @@ RN_API int rn_engine_start(void* hca, int n_ctas, uint64_t idle_timeout_ms, uint
     if (n_ctas == h->engine_ctas || n_ctas <= 0) return 0;
     rn_engine_stop(h);
   }
+  // Anything the caller queued on the legacy default stream (torch.zeros / randn / copies initialising the buffers it is
+  // about to post) must have RUN before the engine becomes resident: legacy-stream work that has not started by then is
+  // held behind the persistent kernel and would execute after the transfers it was meant to precede --
+  // compute-sanitizer's slow launches showed exactly that (zero-fills landing on top of delivered data).  Free when idle.
+  CU_OK(cudaStreamSynchronize(cudaStreamLegacy));
   cudaDeviceProp prop;
   CU_OK(cudaGetDeviceProperties(&prop, h->dev));
   if (n_ctas <= 0) n_ctas = h->engine_ctas > 0 ? h->engine_ctas : 32;

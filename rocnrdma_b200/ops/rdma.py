@@ -27,7 +27,17 @@ def work_stream(ctx, stream=None):
     if stream is not None and int(stream.cuda_stream) != 0:
         return stream
     cur = torch.cuda.current_stream(ctx.device)
-    return cur if int(cur.cuda_stream) != 0 else ctx.stream
+    if int(cur.cuda_stream) != 0:
+        return cur
+    ws = ctx.stream
+    # The caller's tensors were produced on the legacy default stream (torch.zeros / randn / copies): order the work stream
+    # after it, or the kernel races with their initialisation (compute-sanitizer's slower kernels made exactly that visible:
+    # a zero-fill landing after the GEMM had written C).  Not while an engine is resident: anything recorded on the legacy
+    # stream then queues behind the persistent kernel and the poster it gates would never start --
+    # allocate and initialise before engine_start(), as the residency rules say.
+    if not ctx.engine_running:
+        ws.wait_stream(cur)
+    return ws
 
 
 @dataclass

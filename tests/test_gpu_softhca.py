@@ -322,3 +322,39 @@ def test_burst_stream_many_qps_soak(ctx, nbytes):
         c = q.counters()
         assert c["n_wqe"] == iters and c["n_err"] == 0 and c["n_db_order_violations"] == 0
         assert c["n_cqe"] == iters // 16 and c["n_bytes"] == iters * nbytes
+
+
+def test_initialisation_queued_on_the_default_stream_precedes_the_transfer(ctx):
+    """Buffers are usually initialised by torch on the legacy default stream, asynchronously.  Work still queued there when
+    the engine becomes resident would be held behind the persistent kernel and run AFTER the transfer it was meant to
+    precede (seen under compute-sanitizer, whose launches are slow: zero-fills landing on top of delivered data).
+    engine_start() drains the legacy stream first; a long sleep kernel in front of the initialisation makes the
+    late-initialisation case deterministic."""
+    n = 4096
+    src = torch.empty(n, dtype=torch.uint8, device="cuda:0")
+    dst = torch.empty(n, dtype=torch.uint8, device="cuda:0")
+    ms, md = ctx.reg_mr(src), ctx.reg_mr(dst)
+    qp = ctx.loopback_qp(depth=16)
+    torch.cuda.synchronize()
+    torch.cuda._sleep(200_000_000)              # ~0.1 s of default-stream work ahead of the initialisation
+    ops.fill_random(src, seed=99)               # default stream, behind the sleep
+    dst.zero_()
+    ctx.engine_start(ctas=4, idle_timeout_ms=3000)
+    r = ops.rdma_stream(qp, W.OP_RDMA_WRITE, ms, md, n, iters=1)
+    ctx.engine_stop()
+    assert r.ok, r.status
+    assert int(src.sum()) != 0 and torch.equal(src, dst)
+
+
+def test_ops_without_engine_are_ordered_after_the_default_stream(ctx):
+    """ops.* run on the context's non-blocking stream; with no engine resident they first wait for the caller's pending
+    default-stream work, so tensors torch is still initialising are not raced."""
+    M, N, K = 256, 256, 128
+    torch.cuda.synchronize()
+    torch.cuda._sleep(200_000_000)
+    a = torch.randn(M, K, device="cuda:0").to(torch.bfloat16)
+    b = torch.randn(N, K, device="cuda:0").to(torch.bfloat16)
+    c = torch.zeros(M, N, device="cuda:0", dtype=torch.bfloat16)   # would land on top of the product if the GEMM ran first
+    r = ops.gemm_send(ctx, a, b, c)
+    assert r.ok
+    assert torch.allclose(c.float(), a.float() @ b.float().T, rtol=2e-2, atol=0.5)
