@@ -142,6 +142,8 @@ _SIGS = {
     "rn_p2p_put_pages": (i32, [vp, u64, u64]),
     "rn_p2p_live_pins": (i32, [vp]),
     "rn_p2p_pin_size": (C.c_int64, [vp, u64]),
+    "rn_p2p_mmap": (i32, [vp, u64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "rn_p2p_window_kind": (i32, [vp, u64]),
     "rn_p2p_peek": (i32, [vp, u64, vp, u64]),
     "rn_p2p_poke": (i32, [vp, u64, vp, u64]),
     "rn_k_fill_random": (i32, [u64, u64, u64, u64]),

@@ -6,14 +6,17 @@
 //   nvidia_p2p_get_pages(va, len)                  dma-buf export of the range (the pin lives in the fd)
 //   nvidia_p2p_put_pages                           close(fd)
 //   probe pin for is_gpu_address                   cudaPointerGetAttributes
-//   mmap of bus addresses                          peek/poke through cudaMemcpy (the BAR is not mappable
-//                                                  from an unprivileged container)
+//   mmap of bus addresses                          mmap() of the pin's dma-buf fd where the exporter offers it (a real CPU
+//                                                  window through the BAR: rn_p2p_mmap); otherwise peek/poke through
+//                                                  cudaMemcpy -- which proves nothing about the aperture, and says so
+//                                                  (rn_p2p_window_kind)
 //   per-fd list, release-on-close                  per-session list, rn_p2p_close releases leftovers
 // The reference ships only the kernel half (tests/amdp2ptest.c) and no program to drive it.
 #include <cuda_runtime.h>
 #include <errno.h>
 #include <stdint.h>
 #include <string.h>
+#include <sys/mman.h>
 #include <mutex>
 #include <vector>
 
@@ -25,7 +28,7 @@ extern "C" int64_t rn_dmabuf_size(int fd);
 
 namespace {
 constexpr uint64_t kGpuPage = 65536;
-struct Pin { uint64_t handle, va, size; int fd; };
+struct Pin { uint64_t handle, va, size; int fd; void* cpu = nullptr; int map_errno = 0; };
 struct Session {
   std::mutex mu;
   std::vector<Pin> pins;
@@ -46,7 +49,7 @@ RN_API int rn_p2p_close(void* s_) {
   int n = 0;
   {
     std::lock_guard<std::mutex> g(s->mu);
-    for (auto& p : s->pins) { rn_dmabuf_close(p.fd); ++n; }
+    for (auto& p : s->pins) { if (p.cpu) munmap(p.cpu, p.size); rn_dmabuf_close(p.fd); ++n; }
     s->pins.clear();
   }
   delete s;
@@ -85,6 +88,7 @@ RN_API int rn_p2p_put_pages(void* s_, uint64_t addr, uint64_t len) {
   int n = 0;
   for (size_t i = 0; i < s->pins.size();) {
     if (s->pins[i].va == addr && s->pins[i].size == len) {
+      if (s->pins[i].cpu) munmap(s->pins[i].cpu, s->pins[i].size);
       rn_dmabuf_close(s->pins[i].fd);
       s->pins.erase(s->pins.begin() + i);
       ++n;
@@ -110,20 +114,57 @@ RN_API int64_t rn_p2p_pin_size(void* s_, uint64_t handle) {
   return -ENOENT;
 }
 
-// CPU window: read / write `n` bytes at gpu_va, which must lie inside one live pin.
-static int window(Session* s, uint64_t gpu_va, uint64_t n) {
+// The harness's mmap: a CPU mapping of the pinned pages themselves (kmod/b200p2ptest.c remaps the bus addresses; the
+// reference: tests/amdp2ptest.c:336-395).  From userspace the only handle on the pin is its dma-buf, so this is
+// mmap(fd): it works exactly when the exporting driver implements the dma-buf mmap op.  Returns 0 and the address, or
+// -errno of the attempt (remembered per pin: rn_p2p_window_kind reports which window peek / poke are using).
+RN_API int rn_p2p_mmap(void* s_, uint64_t handle, uint64_t* cpu_addr, uint64_t* len) {
+  Session* s = (Session*)s_;
+  std::lock_guard<std::mutex> g(s->mu);
+  for (auto& p : s->pins) {
+    if (p.handle != handle) continue;
+    if (!p.cpu && !p.map_errno) {
+      void* m = mmap(nullptr, p.size, PROT_READ | PROT_WRITE, MAP_SHARED, p.fd, 0);
+      if (m == MAP_FAILED) p.map_errno = errno ? errno : EIO;
+      else p.cpu = m;
+    }
+    if (!p.cpu) return -p.map_errno;
+    *cpu_addr = (uint64_t)p.cpu;
+    *len = p.size;
+    return 0;
+  }
+  return -ENOENT;
+}
+// 1: peek / poke at gpu_va go through a CPU mapping of the pin (the aperture is live); 0: through cudaMemcpy
+RN_API int rn_p2p_window_kind(void* s_, uint64_t gpu_va) {
+  Session* s = (Session*)s_;
   std::lock_guard<std::mutex> g(s->mu);
   for (auto& p : s->pins)
-    if (gpu_va >= p.va && gpu_va + n <= p.va + p.size) return 0;
+    if (gpu_va >= p.va && gpu_va < p.va + p.size) return p.cpu ? 1 : 0;
+  return -EINVAL;
+}
+
+// CPU window: read / write `n` bytes at gpu_va, which must lie inside one live pin.
+static int window(Session* s, uint64_t gpu_va, uint64_t n, uint8_t** cpu) {
+  std::lock_guard<std::mutex> g(s->mu);
+  for (auto& p : s->pins)
+    if (gpu_va >= p.va && gpu_va + n <= p.va + p.size) {
+      *cpu = p.cpu ? (uint8_t*)p.cpu + (gpu_va - p.va) : nullptr;
+      return 0;
+    }
   return -EINVAL;
 }
 RN_API int rn_p2p_peek(void* s, uint64_t gpu_va, void* out, uint64_t n) {
-  int rc = window((Session*)s, gpu_va, n);
+  uint8_t* cpu = nullptr;
+  int rc = window((Session*)s, gpu_va, n, &cpu);
   if (rc) return rc;
+  if (cpu) { memcpy(out, cpu, n); return 0; }
   return cudaMemcpy(out, (const void*)gpu_va, n, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -EIO;
 }
 RN_API int rn_p2p_poke(void* s, uint64_t gpu_va, const void* in, uint64_t n) {
-  int rc = window((Session*)s, gpu_va, n);
+  uint8_t* cpu = nullptr;
+  int rc = window((Session*)s, gpu_va, n, &cpu);
   if (rc) return rc;
+  if (cpu) { memcpy(cpu, in, n); __sync_synchronize(); return 0; }
   return cudaMemcpy((void*)gpu_va, in, n, cudaMemcpyHostToDevice) == cudaSuccess ? 0 : -EIO;
 }

@@ -100,7 +100,9 @@ class DevBackend:
 
 class UserBackend:
     """The same verbs through the CUDA driver API (csrc/reg/p2ptest_user.cc): no kernel module needed.
-    A pin is a dma-buf export of the range; the CPU window is peek/poke through cudaMemcpy."""
+    A pin is a dma-buf export of the range.  The CPU window is an mmap() of that dma-buf where the exporting driver offers
+    one (``map_window``: then peek / poke are CPU loads / stores through the BAR, as in the kernel harness); otherwise peek /
+    poke fall back to cudaMemcpy, which proves nothing about the aperture -- ``window_kind`` says which it was."""
 
     def __init__(self):
         from . import _native as N
@@ -133,6 +135,19 @@ class UserBackend:
     @property
     def live_pins(self) -> int:
         return self._lib.rn_p2p_live_pins(self._s)
+
+    def map_window(self, handle: int):
+        """Try to map the pin into this process (mmap of its dma-buf).  Returns ``(cpu_address, length)`` or raises
+        HarnessError with the errno of the attempt (driver 580: the NVIDIA exporter has no mmap op)."""
+        a, n = C.c_uint64(), C.c_uint64()
+        rc = self._lib.rn_p2p_mmap(self._s, handle, C.byref(a), C.byref(n))
+        if rc:
+            raise HarnessError(-rc, os.strerror(-rc))
+        return a.value, n.value
+
+    def window_kind(self, gpu_va: int) -> str:
+        k = self._lib.rn_p2p_window_kind(self._s, gpu_va)
+        return "dmabuf-mmap (CPU loads/stores through the BAR)" if k == 1 else "cudaMemcpy (no CPU mapping of the pin available)"
 
     def peek(self, gpu_va: int, n: int) -> bytes:
         buf = C.create_string_buffer(n)

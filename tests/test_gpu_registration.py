@@ -52,6 +52,29 @@ def test_twin_pin_multi_pin_and_cpu_window():
     assert be.close() == 1                               # close-with-leaks releases the rest
 
 
+def test_twin_cpu_mapping_of_the_pin_is_attempted_and_reported():
+    """The kernel harness maps the pinned pages into the caller (reference: tests/amdp2ptest.c:336-395).  From userspace the
+    only handle on a pin is its dma-buf: mmap() of that fd is the same window where the exporter implements it.  Either it
+    maps -- then peek / poke are CPU accesses through the BAR and must agree with the GPU's view -- or the attempt fails
+    cleanly with the driver's errno (driver 580: ENOTSUPP, 524) and the twin says it is on the cudaMemcpy fallback."""
+    be = H.UserBackend()
+    t = _buf(2 * PAGE)
+    va = t.data_ptr()
+    g = be.get_pages(va, 2 * PAGE)
+    try:
+        addr, n = be.map_window(g.handle)
+    except H.HarnessError as e:
+        assert e.errno > 0
+        assert be.window_kind(va).startswith("cudaMemcpy")
+    else:
+        assert addr and n == 2 * PAGE
+        assert be.window_kind(va).startswith("dmabuf-mmap")
+    be.poke(va + 8, b"window")
+    torch.cuda.synchronize()
+    assert bytes(t[8:14].cpu().tolist()) == b"window"
+    assert be.close() == 1
+
+
 def test_twin_rejects_misaligned_and_host_ranges():
     be = H.UserBackend()
     t = _buf(4 * PAGE)

@@ -50,6 +50,12 @@ def selftest(backend: str, size: int) -> dict:
         m.close()
     else:
         check("3 the kernel sizes the pinned object correctly", be.pin_size(g.handle) == 4 * PAGE)
+        try:                                  # the harness's mmap, from userspace: a CPU mapping of the pin's dma-buf
+            be.map_window(g.handle)
+            res["cpu_window"] = be.window_kind(va)
+        except H.HarnessError as e:
+            res["cpu_window"] = f"{be.window_kind(va)}; mmap(dma-buf fd) failed: errno {e.errno} ({e.strerror})"
+        print("  cpu window:", res["cpu_window"])
         be.poke(va, b"BARwrite")
         torch.cuda.synchronize()
         check("3 CPU window write lands in HBM", bytes(t[:8].cpu().tolist()) == b"BARwrite")

@@ -26,3 +26,10 @@ for m in re.finditer(r"\t\tFunction : (\S+)\n(.*?)(?=\n\t\tFunction : |\Z)", txt
 json.dump(summary, open(os.path.join(out, "summary.json"), "w"), indent=1)
 for k, v in summary.items():
     print(k, v["instructions"], v["blackwell"])
+
+# the register / spill / shared-memory report of the same build, next to the listings (the build writes it into the
+# git-ignored lib directory)
+import shutil
+_src = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "rocnrdma_b200", "lib", "ptxas_info.txt")
+if os.path.exists(_src):
+    shutil.copy(_src, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ptxas_info.txt"))
