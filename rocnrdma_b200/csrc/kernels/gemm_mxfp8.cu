@@ -62,8 +62,20 @@ struct MxArgs {
   uint32_t a_rows_per_rec, b_rows_per_rec;
   __nv_bfloat16* c;
   uint32_t M, N, K;
-  unsigned long long* out;   // [status, t_start, t_end, tiles, 0...]
+  unsigned long long* out;   // [status, t_start, t_end, tiles, 0...]: mapped pinned HOST memory -- written by the last CTA only
+  unsigned int* done;        // device scratch (zeroed, self-cleaning): CTAs finished
 };
+// Result words live in host memory: one atomic per CTA there (the first version's atomicMax of the end time) is a PCIe
+// round trip each -- 148 of them serialised cost ~150 us per launch, more than a 4096^3 product.  Count in device memory,
+// let the last CTA write.
+__device__ __forceinline__ void mx_finish(const MxArgs& g, bool aborted, unsigned long long t_start, uint32_t n_tiles, uint32_t variant) {
+  if (aborted) g.out[0] = (unsigned long long)(long long)WAIT_TIMEOUT;
+  __threadfence();
+  if (atomicAdd(g.done, 1u) + 1 != gridDim.x) return;
+  g.out[1] = t_start; g.out[3] = n_tiles; g.out[6] = variant;
+  g.out[2] = globaltimer_ns();
+  *g.done = 0;
+}
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(n)); }
@@ -312,12 +324,328 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
   }
-  if (threadIdx.x == 64) {
-    if (s.abort) g.out[0] = (unsigned long long)(long long)WAIT_TIMEOUT;
-    if (blockIdx.x == 0) { g.out[1] = t_start; g.out[3] = n_tiles; }
-    __threadfence();
-    atomicMax(&g.out[2], globaltimer_ns());
+  if (threadIdx.x == 64) mx_finish(g, s.abort != 0, t_start, n_tiles, 1u);
+}
+
+
+// ==================================================================== CTA-pair variant (cta_group::2)
+// The single-CTA kernel above moves 32 KiB of operands per 4.2 MFLOP: at fp8 rates that is L2-bandwidth-bound (measured:
+// 1.28 PFLOP/s at 8192^3 = 10 TB/s of L2 -> SM traffic).  Here two CTAs of a cluster compute a 256 x 256 tile: each loads its
+// 128 rows of A and HALF of B (32 KiB per 8.4 MFLOP per CTA: half the traffic per FLOP), the leader issues M = 256 MMAs.
+//   * The accumulator is two N = 128 halves (TMEM columns 0-127 / 128-255): one MMA per half and k32.  Every MMA then has
+//     exactly one 128-row scale chunk for B -- the shape the single-CTA kernel validated -- and the halves are handed back
+//     to the issuer separately, which runs half 0 up to STAGES - 1 k-blocks ahead while half 1 is still being drained.
+//   * With cta_group::2 an N = 128 MMA takes B rows 0-63 from the leader's shared memory and 64-127 from the partner's, so
+//     CTA r loads, for half h, tile columns h * 128 + r * 64 .. + 64 (two 64-row TMA boxes per stage).
+//   * Scale factors: tcgen05.cp.cta_group::2 is issued by the leader and copies, in EACH CTA, that CTA's own chunk into
+//     its own TMEM (operand descriptors of a pair instruction are CTA-relative).  Both CTAs therefore build chunks: A
+//     scales for their own 128 rows, B scales for all 256 columns.  The partner's chunks must be complete before the
+//     leader issues the copies: its four loader warps meet at a named barrier and one thread rings a 16-byte
+//     shared::cta -> shared::cluster bulk copy whose completion is counted on the LEADER's full barrier -- a hardware
+//     signal, no release-scoped remote arrive on anybody's critical path (that pattern halved the bf16 pair kernel once).
+constexpr int STAGES2 = 6;
+constexpr int BN2 = 256;
+struct alignas(1024) Smem2 {
+  uint8_t a[STAGES2][A_STAGE];                 // this CTA's 128 rows of A
+  uint8_t b[STAGES2][2][B_STAGE / 2];          // [half][64 rows]: this CTA's share of B for each accumulator half
+  alignas(128) uint8_t sfa[STAGES2][SF_STAGE];
+  alignas(128) uint8_t sfb[STAGES2][2][SF_STAGE];
+  alignas(16) uint8_t bell[STAGES2][16];       // landing pad of the partner's "chunks written" doorbell copy (leader only)
+  alignas(8) uint64_t full[STAGES2], empty[STAGES2], tfull, tempty[2];
+  uint32_t tmem_base;
+  volatile int abort;
+};
+constexpr uint32_t kSfCol0_2 = 256;            // scale factors above the 256 accumulator columns: 16 columns per stage
+
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t cta_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(s32(smem_dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(s32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void utccp_32x128b_warpx4_2sm(uint32_t tmem_dst, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::2.32x128b.warpx4 [%0], %1;" ::"r"(tmem_dst), "l"(sdesc) : "memory");
+}
+__device__ __forceinline__ uint32_t mx_idesc2(uint32_t sf_id) {    // M = 256 (both CTAs), N = 128
+  return (sf_id << 4) | ((uint32_t)(128 >> 3) << 17) | (1u << 23) | ((uint32_t)(256 >> 4) << 24) | (sf_id << 29);
+}
+__device__ __forceinline__ void umma_mxf8_2sm(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t tsfa, uint32_t tsfb, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::2.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
+               ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(tsfa), "r"(tsfb) : "memory");
+}
+// 16 bytes of this CTA's shared memory -> the leader's, completion counted (in bytes) on the leader's barrier
+__device__ __forceinline__ void ring_bell(uint32_t dst_cluster, const void* src_cta, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], 16, [%2];"
+               ::"r"(dst_cluster), "r"(s32(src_cta)), "r"(bar_cluster) : "memory");
+}
+template <typename S>
+__device__ __forceinline__ bool mbar_wait_t(S& s, uint64_t* b, uint32_t parity) {
+  if (mbar_try(b, parity)) return true;
+  unsigned long long t0 = globaltimer_ns();
+  unsigned n = 0;
+  while (!mbar_try(b, parity)) {
+    if ((++n & 255) == 0) {
+      if (s.abort) return false;
+      if (globaltimer_ns() - t0 > kWaitNs) { s.abort = 1; return false; }
+    }
   }
+  return true;
+}
+// grouped rasterisation (as gemm_send.cu): `group` M tiles advance together across N so concurrent clusters share B in L2
+__device__ __forceinline__ void tile_coords2(uint32_t t, uint32_t m_tiles, uint32_t n_tiles_n, uint32_t group, uint32_t* m, uint32_t* n) {
+  const uint32_t per_group = group * n_tiles_n;
+  const uint32_t grp = t / per_group, r = t % per_group;
+  const uint32_t m0 = grp * group;
+  const uint32_t gm = min(group, m_tiles - m0);
+  *m = m0 + r % gm;
+  *n = r / gm;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_mxfp8_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ MxArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  Smem2& s = *reinterpret_cast<Smem2*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();
+  const bool leader = rank == 0;
+  const unsigned long long t_start = globaltimer_ns();
+  const uint32_t m_tiles = (g.M + 2 * BM - 1) / (2 * BM), n_tiles_n = (g.N + BN2 - 1) / BN2, k_blks = (g.K + BK - 1) / BK;
+  const uint32_t n_tiles = m_tiles * n_tiles_n, ks = g.K / 32;
+  const uint32_t n_units = gridDim.x / 2, unit = blockIdx.x / 2;
+  constexpr uint32_t kGroup = 8;
+
+  if (threadIdx.x == 0) {
+    // full: the producer's expect_tx arrive + the LEADER's four loader warps; the partner's loaders are the 16 doorbell bytes
+    for (int i = 0; i < STAGES2; ++i) { mbar_init(&s.full[i], 1 + 4); mbar_init(&s.empty[i], 1); }
+    mbar_init(&s.tfull, 1);
+    mbar_init(&s.tempty[0], 8); mbar_init(&s.tempty[1], 8);
+    s.abort = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&s.tmem_base)), "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = s.tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs)
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (uint32_t tile = unit; tile < n_tiles && !s.abort; tile += n_units) {
+        uint32_t mt, nt;
+        tile_coords2(tile, m_tiles, n_tiles_n, kGroup, &mt, &nt);
+        const uint32_t ar = (mt * 2 + rank) * BM;
+        for (uint32_t kb = 0; kb < k_blks; ++kb) {
+          if (!mbar_wait_t(s, &s.empty[stage], phase ^ 1)) goto producer2_done;
+          const uint32_t lbar = mapa(s32(&s.full[stage]), 0);
+          if (leader) mbar_expect_tx(&s.full[stage], 2 * (A_STAGE + B_STAGE) + 16);
+          tma_load_3d_2sm(s.a[stage], &tmap_a, lbar, (int)(kb * BK), (int)(ar % g.a_rows_per_rec), (int)(ar / g.a_rows_per_rec));
+#pragma unroll
+          for (uint32_t h = 0; h < 2; ++h) {
+            const uint32_t br = nt * BN2 + h * 128 + rank * 64;             // 64-row boxes never straddle records (rows_per_rec % 128 == 0)
+            tma_load_3d_2sm(s.b[stage][h], &tmap_b, lbar, (int)(kb * BK), (int)(br % g.b_rows_per_rec), (int)(br / g.b_rows_per_rec));
+          }
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  producer2_done:
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader only)
+    if (leader && lane == 0) {
+      uint32_t stage = 0, phase = 0, tphase = 0;
+      auto sf_cols = [&](uint32_t st) { return tmem_base + kSfCol0_2 + st * 16; };
+      auto copy_scales = [&](uint32_t st) {                                   // SFA, SFB of half 0, SFB of half 1: in both CTAs, each from its own chunks
+        utccp_32x128b_warpx4_2sm(sf_cols(st), smem_desc_sf(s.sfa[st]));
+        utccp_32x128b_warpx4_2sm(sf_cols(st) + 4, smem_desc_sf(s.sfb[st][0]));
+        utccp_32x128b_warpx4_2sm(sf_cols(st) + 8, smem_desc_sf(s.sfb[st][1]));
+      };
+      auto issue_half = [&](uint32_t st, uint32_t h, bool first) {
+        const uint64_t da = smem_desc_sw128(s.a[st]), db = smem_desc_sw128(s.b[st][h]);
+        const uint32_t tsfa = sf_cols(st), tsfb = sf_cols(st) + 4 + h * 4;
+#pragma unroll
+        for (uint32_t k = 0; k < BK / UMMA_K; ++k)
+          umma_mxf8_2sm(tmem_base + h * 128, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), mx_idesc2(k), tsfa | (k << 30), tsfb | (k << 30), !first || k != 0);
+      };
+      for (uint32_t tile = unit; tile < n_tiles && !s.abort; tile += n_units) {
+        const uint32_t ahead = k_blks < (uint32_t)(STAGES2 - 1) ? k_blks : (uint32_t)(STAGES2 - 1);
+        if (!mbar_wait_t(s, &s.tempty[0], tphase ^ 1)) goto mma2_done;
+        tc_fence_after();
+        uint32_t st = stage, ph = phase;
+        for (uint32_t i = 0; i < ahead; ++i) {                                 // half 0 runs ahead while half 1 is still being drained
+          if (!mbar_wait_t(s, &s.full[st], ph)) goto mma2_done;
+          tc_fence_after();
+          copy_scales(st);
+          issue_half(st, 0, i == 0);
+          if (++st == STAGES2) { st = 0; ph ^= 1; }
+        }
+        if (!mbar_wait_t(s, &s.tempty[1], tphase ^ 1)) goto mma2_done;
+        tc_fence_after();
+        for (uint32_t i = 0; i < ahead; ++i) {
+          issue_half(stage, 1, i == 0);
+          tc_commit_2sm(&s.empty[stage]);
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+        for (uint32_t kb = ahead; kb < k_blks; ++kb) {
+          if (!mbar_wait_t(s, &s.full[stage], phase)) goto mma2_done;
+          tc_fence_after();
+          copy_scales(stage);
+          issue_half(stage, 0, false);
+          issue_half(stage, 1, false);
+          tc_commit_2sm(&s.empty[stage]);
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_2sm(&s.tfull);
+        tphase ^= 1;
+      }
+    }
+  mma2_done:
+    __syncwarp();
+  } else if (warp < 6) {
+    // ===================== epilogue (both CTAs: their own 128 rows)
+    const uint32_t q = warp & 3;
+    uint32_t tphase = 0;
+    for (uint32_t tile = unit; tile < n_tiles; tile += n_units) {
+      uint32_t mt, nt;
+      tile_coords2(tile, m_tiles, n_tiles_n, kGroup, &mt, &nt);
+      if (!mbar_wait_t(s, &s.tfull, tphase)) break;
+      tphase ^= 1;
+      tc_fence_after();
+      const uint32_t row = (mt * 2 + rank) * BM + q * 32 + lane;
+      __nv_bfloat16* crow = g.c + (size_t)row * g.N + (size_t)nt * BN2;
+#pragma unroll 1
+      for (uint32_t h = 0; h < 2; ++h) {
+        const uint32_t taddr = tmem_base + ((q * 32u) << 16) + h * 128;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          tmem_ld_wait();
+          if (c == 3) {                                                        // the half is in registers: hand it back before storing
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (leader) mbar_arrive(&s.tempty[h]);
+              else mbar_arrive_remote(mapa(s32(&s.tempty[h]), 0));
+            }
+          }
+          const uint32_t col0 = nt * BN2 + h * 128 + c * 32;
+          if (row < g.M && col0 < g.N) {
+            __nv_bfloat16* dstp = crow + h * 128 + c * 32;
+            if (col0 + 32 <= g.N && (g.N & 7) == 0) {
+              uint4* dst = reinterpret_cast<uint4*>(dstp);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                dst[j] = make_uint4(pack_bf16(r[8 * j], r[8 * j + 1]), pack_bf16(r[8 * j + 2], r[8 * j + 3]), pack_bf16(r[8 * j + 4], r[8 * j + 5]),
+                                    pack_bf16(r[8 * j + 6], r[8 * j + 7]));
+            } else {
+              for (int j = 0; j < 32 && col0 + j < g.N; ++j) dstp[j] = __float2bfloat16_rn(__uint_as_float(r[j]));
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== scale loaders (warps 6-9, both CTAs): thread (w, lane) owns row w * 32 + lane of this CTA's A rows and
+    // of each 128-column half of B
+    const uint32_t w = warp - 6;
+    uint32_t stage = 0, phase = 0;
+    auto ld16 = [&](const uint8_t* base, uint64_t rec_stride, uint32_t rows_per_rec, uint32_t rows, uint32_t row, uint32_t kb) -> uint4 {
+      if (row < rows && kb * 4 + 16 <= ks) {
+        const uint8_t* p = base + (uint64_t)(row / rows_per_rec) * rec_stride + (uint64_t)(row % rows_per_rec) * ks + (uint64_t)kb * 4;
+        if (((uintptr_t)p & 15) == 0) return __ldg(reinterpret_cast<const uint4*>(p));
+      }
+      return make_uint4(load_scales(base, rec_stride, rows_per_rec, rows, ks, row, kb), load_scales(base, rec_stride, rows_per_rec, rows, ks, row, kb + 1),
+                        load_scales(base, rec_stride, rows_per_rec, rows, ks, row, kb + 2), load_scales(base, rec_stride, rows_per_rec, rows, ks, row, kb + 3));
+    };
+    const uint32_t bell_dst = mapa(s32(&s.bell[0][0]), 0);
+    // rows this thread serves for a tile, and the first group (k-blocks 0-3) of their scales
+    struct Rows { uint32_t a, b0, b1; };
+    auto rows_of = [&](uint32_t tile) -> Rows {
+      uint32_t mt, nt;
+      tile_coords2(tile, m_tiles, n_tiles_n, kGroup, &mt, &nt);
+      const uint32_t b0 = nt * BN2 + w * 32 + lane;
+      return Rows{(mt * 2 + rank) * BM + w * 32 + lane, b0, b0 + 128};
+    };
+    uint4 ca = make_uint4(0, 0, 0, 0), cb0 = ca, cb1 = ca;
+    if (unit < n_tiles) {
+      const Rows r0 = rows_of(unit);
+      ca = ld16(g.a_s, g.a_rec_stride, g.a_rows_per_rec, g.M, r0.a, 0);
+      cb0 = ld16(g.b_s, g.b_rec_stride, g.b_rows_per_rec, g.N, r0.b0, 0);
+      cb1 = ld16(g.b_s, g.b_rec_stride, g.b_rows_per_rec, g.N, r0.b1, 0);
+    }
+    for (uint32_t tile = unit; tile < n_tiles && !s.abort; tile += n_units) {
+      const Rows rw = rows_of(tile);
+      for (uint32_t kb0 = 0; kb0 < k_blks; kb0 += 4) {
+        // the next group's loads are in flight while this one is handed over -- at the end of a tile that is the NEXT TILE's
+        // first group (a blocking load there put ~1 us per tile on the issuer's critical path)
+        uint4 na = ca, nb0 = cb0, nb1 = cb1;
+        if (kb0 + 4 < k_blks) {
+          na = ld16(g.a_s, g.a_rec_stride, g.a_rows_per_rec, g.M, rw.a, kb0 + 4);
+          nb0 = ld16(g.b_s, g.b_rec_stride, g.b_rows_per_rec, g.N, rw.b0, kb0 + 4);
+          nb1 = ld16(g.b_s, g.b_rec_stride, g.b_rows_per_rec, g.N, rw.b1, kb0 + 4);
+        } else if (tile + n_units < n_tiles) {
+          const Rows rn = rows_of(tile + n_units);
+          na = ld16(g.a_s, g.a_rec_stride, g.a_rows_per_rec, g.M, rn.a, 0);
+          nb0 = ld16(g.b_s, g.b_rec_stride, g.b_rows_per_rec, g.N, rn.b0, 0);
+          nb1 = ld16(g.b_s, g.b_rec_stride, g.b_rows_per_rec, g.N, rn.b1, 0);
+        }
+        const uint32_t wa[4] = {ca.x, ca.y, ca.z, ca.w}, wb0[4] = {cb0.x, cb0.y, cb0.z, cb0.w}, wb1[4] = {cb1.x, cb1.y, cb1.z, cb1.w};
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) {
+          if (kb0 + j >= k_blks) break;
+          if (!mbar_wait_t(s, &s.empty[stage], phase ^ 1)) goto loader2_done;
+          *reinterpret_cast<uint32_t*>(&s.sfa[stage][lane * 16 + w * 4]) = wa[j];
+          *reinterpret_cast<uint32_t*>(&s.sfb[stage][0][lane * 16 + w * 4]) = wb0[j];
+          *reinterpret_cast<uint32_t*>(&s.sfb[stage][1][lane * 16 + w * 4]) = wb1[j];
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");         // generic-proxy writes -> visible to tcgen05.cp
+          if (leader) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s.full[stage]);
+          } else {
+            asm volatile("bar.sync 2, 128;" ::: "memory");                    // all four loader warps of this CTA have written and fenced
+            if (threadIdx.x == 6 * 32) ring_bell(bell_dst + stage * 16, s.sfa[stage], mapa(s32(&s.full[stage]), 0));
+          }
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+        ca = na; cb0 = nb0; cb1 = nb1;
+      }
+    }
+  loader2_done:
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+  }
+  if (threadIdx.x == 64) mx_finish(g, s.abort != 0, t_start, n_tiles, 2u);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -334,13 +662,13 @@ EncodeTiledFn encode_tiled() {
   return fn;
 }
 // fp8 operand [rows, K] held in n_rec records of rows_per_rec rows, rec_stride bytes apart: a 3-D map (K, row, record)
-int make_map3(CUtensorMap* m, const void* base, uint64_t rows, uint64_t K, uint64_t rows_per_rec, uint64_t rec_stride) {
+int make_map3(CUtensorMap* m, const void* base, uint64_t rows, uint64_t K, uint64_t rows_per_rec, uint64_t rec_stride, uint32_t box_rows = BM) {
   EncodeTiledFn fn = encode_tiled();
   if (!fn) return -38;
   const uint64_t n_rec = (rows + rows_per_rec - 1) / rows_per_rec;
   cuuint64_t dims[3] = {K, rows_per_rec < rows ? rows_per_rec : rows, n_rec};
   cuuint64_t strides[2] = {K, rec_stride};
-  cuuint32_t box[3] = {BK, BM, 1};
+  cuuint32_t box[3] = {BK, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -354,7 +682,7 @@ int make_map3(CUtensorMap* m, const void* base, uint64_t rows, uint64_t K, uint6
 // plain matrix).  K % 32 == 0, K % 16 == 0 for the TMA row stride; M and N are free (bf16 C rows of N elements).
 RN_API int rn_k_gemm_mxfp8(uint64_t stream, int grid, uint64_t a_q, uint64_t a_s, uint32_t a_rows_per_rec, uint64_t a_rec_stride, uint64_t b_q,
                            uint64_t b_s, uint32_t b_rows_per_rec, uint64_t b_rec_stride, uint64_t c, uint32_t M, uint32_t N, uint32_t K,
-                           uint64_t out_dev) {
+                           uint64_t out_dev, uint32_t cta_group, uint64_t done_dev) {
   if (!M || !N || !K || (K % 32) || (K % 16)) return -22;
   if ((a_q | b_q) & 15 || (c & 1)) return -22;
   if (!a_rows_per_rec) a_rows_per_rec = M;
@@ -373,10 +701,26 @@ RN_API int rn_k_gemm_mxfp8(uint64_t stream, int grid, uint64_t a_q, uint64_t a_s
   g.a_rec_stride = a_rec_stride; g.b_rec_stride = b_rec_stride; g.a_rows_per_rec = a_rows_per_rec; g.b_rows_per_rec = b_rows_per_rec;
   g.c = (__nv_bfloat16*)c; g.M = M; g.N = N; g.K = K;
   g.out = (unsigned long long*)out_dev;
+  g.done = (unsigned int*)done_dev;
+  if (!done_dev) return -22;
   unsigned long long* o = (unsigned long long*)out_dev;
   for (int i = 0; i < 8; ++i) o[i] = 0;
-  const uint32_t n_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   if (grid <= 0) grid = 148;
+  // cta_group: 2 = CTA-pair kernel (256 x 256 per pair), 1 = single-CTA kernel (128 x 128), 0 = pair when the matrix has more
+  // than one 128-row block (a pair tile hanging over the last rows computes zeros: correct, wasted)
+  if ((cta_group == 2 || (cta_group == 0 && M > BM)) && grid >= 2) {
+    rc = make_map3(&mb, (const void*)b_q, N, K, b_rows_per_rec, b_rec_stride >= 16 ? (b_rec_stride + 15) / 16 * 16 : 16, 64);
+    if (rc) return rc;
+    const uint32_t n_tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN2 - 1) / BN2);
+    grid &= ~1;
+    if ((uint32_t)grid > 2 * n_tiles) grid = (int)(2 * n_tiles);
+    const size_t smem = sizeof(Smem2) + 1024;
+    cudaError_t e = cudaFuncSetAttribute(gemm_mxfp8_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return -(int)e - 1000;
+    gemm_mxfp8_pair_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ma, mb, g);
+    return (int)cudaGetLastError();
+  }
+  const uint32_t n_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   if ((uint32_t)grid > n_tiles) grid = (int)n_tiles;
   const size_t smem = sizeof(Smem) + 1024;
   cudaError_t e = cudaFuncSetAttribute(gemm_mxfp8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -389,5 +733,7 @@ extern "C" __attribute__((visibility("default"))) void rn_preload_gemm_mx() {
   cudaFuncAttributes at;
   cudaFuncGetAttributes(&at, gemm_mxfp8_kernel);
   cudaFuncSetAttribute(gemm_mxfp8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Smem) + 1024));
+  cudaFuncGetAttributes(&at, gemm_mxfp8_pair_kernel);
+  cudaFuncSetAttribute(gemm_mxfp8_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Smem2) + 1024));
   encode_tiled();
 }

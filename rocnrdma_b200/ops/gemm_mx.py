@@ -66,16 +66,23 @@ class MxResult:
         return 2.0 * self.M * self.N * self.K / max(self.device_ns, 1) / 1e3
 
 
-def gemm_mxfp8(ctx, a: MxOperand, b: MxOperand, c: torch.Tensor, grid: int = 0, stream=None, sync: bool = True, scratch_slot: int = 3):
+def gemm_mxfp8(ctx, a: MxOperand, b: MxOperand, c: torch.Tensor, grid: int = 0, stream=None, sync: bool = True, scratch_slot: int = 3,
+               cta_group: int = 0):
     """``c[M,N] (bf16) = dequant(a)[M,K] @ dequant(b)[N,K].T`` with the block scales applied by the tensor core.
-    Any M and N; K a multiple of 32 (one MX block) and of 16 bytes."""
+    Any M and N; K a multiple of 32 (one MX block) and of 16 bytes.
+    ``cta_group``: 2 = CTA-pair kernel (256 x 256 per pair, half the operand traffic per FLOP), 1 = single-CTA kernel
+    (128 x 128), 0 = pair for M > 128.  ``RN_MX_CTA_GROUP`` overrides (A/B switch)."""
+    import os
+    if os.environ.get("RN_MX_CTA_GROUP"):
+        cta_group = int(os.environ["RN_MX_CTA_GROUP"])
     M, Nn, K = a.rows, b.rows, a.K
     assert b.K == K and c.dtype == torch.bfloat16 and tuple(c.shape) == (M, Nn) and c.is_contiguous()
     lib = N.load()
     ws = work_stream(ctx, stream)
     out_addr, out_view = ctx.scratch(64, offset=4096 + scratch_slot * 64)
+    done = ctx.dev_scratch(64, offset=scratch_slot * (256 << 10))          # zeroed device counter, cleaned by the kernel
     rc = lib.rn_k_gemm_mxfp8(_stream_ptr(ws), grid, a.q_ptr, a.s_ptr, a.rows_per_rec, a.rec_stride, b.q_ptr, b.s_ptr, b.rows_per_rec,
-                             b.rec_stride, c.data_ptr(), M, Nn, K, out_addr)
+                             b.rec_stride, c.data_ptr(), M, Nn, K, out_addr, cta_group, done)
     if rc:
         raise N.NativeError(f"gemm_mxfp8 launch failed ({rc})")
     if not sync:

@@ -25,20 +25,22 @@ def _check(c, aq, as_, bq, bs, K):
     assert err <= tol, (err, tol)
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (128, 128, 512), (256, 384, 256), (1024, 512, 1024)])
-def test_mxfp8_gemm_matches_dequantised_fp32_reference(ctx, M, N, K):
+@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (128, 128, 512), (256, 384, 256), (1024, 512, 1024), (2048, 2304, 1152)])
+def test_mxfp8_gemm_matches_dequantised_fp32_reference(ctx, M, N, K, cta_group):
     a, b = _rand(M, K), _rand(N, K)
     (aq, as_), (bq, bs) = MX.quantize_mx(a), MX.quantize_mx(b)
     c = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
-    r = ops.gemm_mxfp8(ctx, MX.MxOperand.from_tensors(aq, as_), MX.MxOperand.from_tensors(bq, bs), c)
+    r = ops.gemm_mxfp8(ctx, MX.MxOperand.from_tensors(aq, as_), MX.MxOperand.from_tensors(bq, bs), c, cta_group=cta_group)
     assert r.ok, r.status
     _check(c, aq, as_, bq, bs, K)
 
 
-def test_mxfp8_scale_bytes_are_applied_per_row_and_per_block(ctx):
+@pytest.mark.parametrize("cta_group,M,N", [(1, 128, 128), (2, 256, 256), (2, 512, 768)])
+def test_mxfp8_scale_bytes_are_applied_per_row_and_per_block(ctx, cta_group, M, N):
     """All data = 1.0 (e4m3 0x38); only the scales differ.  C[i][j] = sum_k 2^(sa[i][k] + sb[j][k]): any mix-up of row,
-    k-block or operand in the scale-factor path changes the answer by powers of two."""
-    M = N = 128
+    k-block, operand -- or, in the pair kernel, of CTA and accumulator half -- in the scale-factor path changes the answer
+    by powers of two."""
     K = 256
     aq = torch.full((M, K), 0x38, dtype=torch.uint8, device="cuda")
     bq = torch.full((N, K), 0x38, dtype=torch.uint8, device="cuda")
@@ -46,19 +48,20 @@ def test_mxfp8_scale_bytes_are_applied_per_row_and_per_block(ctx):
     eb = torch.randint(-3, 4, (N, K // 32), device="cuda")
     as_, bs = (ea + 127).to(torch.uint8), (eb + 127).to(torch.uint8)
     c = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
-    assert ops.gemm_mxfp8(ctx, MX.MxOperand.from_tensors(aq, as_), MX.MxOperand.from_tensors(bq, bs), c).ok
+    assert ops.gemm_mxfp8(ctx, MX.MxOperand.from_tensors(aq, as_), MX.MxOperand.from_tensors(bq, bs), c, cta_group=cta_group).ok
     ref = 32.0 * (torch.exp2(ea.float()) @ torch.exp2(eb.float()).T)
     assert torch.allclose(c.float(), ref, rtol=1e-2, atol=0), (c.float() - ref).abs().max()
 
 
-@pytest.mark.parametrize("M,N,K", [(200, 136, 160), (130, 72, 96), (64, 300, 32)])
-def test_mxfp8_ragged_shapes(ctx, M, N, K):
+@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("M,N,K", [(200, 136, 160), (130, 72, 96), (64, 300, 32), (700, 520, 416)])
+def test_mxfp8_ragged_shapes(ctx, M, N, K, cta_group):
     """TMA zero-fills the out-of-bounds rows and the K tail; the epilogue bounds-checks its stores."""
     a, b = _rand(M, K), _rand(N, K)
     (aq, as_), (bq, bs) = MX.quantize_mx(a), MX.quantize_mx(b)
     pad = torch.full((M + 1, N), 7.0, device="cuda", dtype=torch.bfloat16)     # a canary row behind C
     c = pad[:M]
-    r = ops.gemm_mxfp8(ctx, MX.MxOperand.from_tensors(aq, as_), MX.MxOperand.from_tensors(bq, bs), c)
+    r = ops.gemm_mxfp8(ctx, MX.MxOperand.from_tensors(aq, as_), MX.MxOperand.from_tensors(bq, bs), c, cta_group=cta_group)
     assert r.ok, r.status
     _check(c, aq, as_, bq, bs, K)
     assert torch.all(pad[M] == 7.0), "the epilogue wrote past the last row"
