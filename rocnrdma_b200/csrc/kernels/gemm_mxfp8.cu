@@ -331,27 +331,31 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 // ==================================================================== CTA-pair variant (cta_group::2)
 // The single-CTA kernel above moves 32 KiB of operands per 4.2 MFLOP: at fp8 rates that is L2-bandwidth-bound (measured:
 // 1.28 PFLOP/s at 8192^3 = 10 TB/s of L2 -> SM traffic).  Here two CTAs of a cluster compute a 256 x 256 tile: each loads its
-// 128 rows of A and HALF of B (32 KiB per 8.4 MFLOP per CTA: half the traffic per FLOP), the leader issues M = 256 MMAs.
-//   * The accumulator is two N = 128 halves (TMEM columns 0-127 / 128-255): one MMA per half and k32.  Every MMA then has
-//     exactly one 128-row scale chunk for B -- the shape the single-CTA kernel validated -- and the halves are handed back
-//     to the issuer separately, which runs half 0 up to STAGES - 1 k-blocks ahead while half 1 is still being drained.
-//   * With cta_group::2 an N = 128 MMA takes B rows 0-63 from the leader's shared memory and 64-127 from the partner's, so
-//     CTA r loads, for half h, tile columns h * 128 + r * 64 .. + 64 (two 64-row TMA boxes per stage).
+// 128 rows of A and HALF of B (32 KiB per 8.4 MFLOP per CTA: half the traffic per FLOP), the leader issues ONE
+// M = 256, N = 256, K = 32 MMA per k32.
+//   * N = 256 matters at fp8 rates: a first version with two N = 128 MMAs per k32 (two accumulator halves, handed back
+//     separately) ran every MMA at half speed -- the issuer's own clock showed ~125 cycles per instruction where 64 were
+//     due.  Each N = 128 instruction re-reads the CTA's 4 KiB of A for 4 KiB of B: 8 KiB per 64 cycles is the whole
+//     128 B/cycle shared-memory port, with TMA writing into it at the same time.  N = 256 reads 12 KiB per 128 cycles.
+//   * TMEM: one 256-column accumulator (single-buffered: 512 columns do not hold two of them plus the scale factors).
+//     The epilogue releases it the moment its last values are in registers; what stays exposed is the TMEM drain
+//     (~1.5 k cycles per tile, see gemm_send.cu).
 //   * Scale factors: tcgen05.cp.cta_group::2 is issued by the leader and copies, in EACH CTA, that CTA's own chunk into
 //     its own TMEM (operand descriptors of a pair instruction are CTA-relative).  Both CTAs therefore build chunks: A
-//     scales for their own 128 rows, B scales for all 256 columns.  The partner's chunks must be complete before the
-//     leader issues the copies: its four loader warps meet at a named barrier and one thread rings a 16-byte
-//     shared::cta -> shared::cluster bulk copy whose completion is counted on the LEADER's full barrier -- a hardware
-//     signal, no release-scoped remote arrive on anybody's critical path (that pattern halved the bf16 pair kernel once).
+//     scales for their own 128 rows, B scales for all 256 columns (two chunks, adjacent 4-column groups in TMEM).  The
+//     partner's chunks must be complete before the leader issues the copies: its four loader warps meet at a named
+//     barrier and one thread rings a 16-byte shared::cta -> shared::cluster bulk copy whose completion is counted on the
+//     LEADER's full barrier -- a hardware signal, no release-scoped remote arrive on anybody's critical path (that
+//     pattern halved the bf16 pair kernel once).
 constexpr int STAGES2 = 6;
 constexpr int BN2 = 256;
 struct alignas(1024) Smem2 {
   uint8_t a[STAGES2][A_STAGE];                 // this CTA's 128 rows of A
-  uint8_t b[STAGES2][2][B_STAGE / 2];          // [half][64 rows]: this CTA's share of B for each accumulator half
+  uint8_t b[STAGES2][B_STAGE];                 // this CTA's 128 of the tile's 256 B rows (leader: columns 0-127, partner: 128-255)
   alignas(128) uint8_t sfa[STAGES2][SF_STAGE];
   alignas(128) uint8_t sfb[STAGES2][2][SF_STAGE];
   alignas(16) uint8_t bell[STAGES2][16];       // landing pad of the partner's "chunks written" doorbell copy (leader only)
-  alignas(8) uint64_t full[STAGES2], empty[STAGES2], tfull, tempty[2];
+  alignas(8) uint64_t full[STAGES2], empty[STAGES2], tfull, tempty;
   uint32_t tmem_base;
   volatile int abort;
 };
@@ -380,8 +384,8 @@ __device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {
 __device__ __forceinline__ void utccp_32x128b_warpx4_2sm(uint32_t tmem_dst, uint64_t sdesc) {
   asm volatile("tcgen05.cp.cta_group::2.32x128b.warpx4 [%0], %1;" ::"r"(tmem_dst), "l"(sdesc) : "memory");
 }
-__device__ __forceinline__ uint32_t mx_idesc2(uint32_t sf_id) {    // M = 256 (both CTAs), N = 128
-  return (sf_id << 4) | ((uint32_t)(128 >> 3) << 17) | (1u << 23) | ((uint32_t)(256 >> 4) << 24) | (sf_id << 29);
+__device__ __forceinline__ uint32_t mx_idesc2(uint32_t sf_id) {    // M = 256 (both CTAs), N = 256
+  return (sf_id << 4) | ((uint32_t)(256 >> 3) << 17) | (1u << 23) | ((uint32_t)(256 >> 4) << 24) | (sf_id << 29);
 }
 __device__ __forceinline__ void umma_mxf8_2sm(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t tsfa, uint32_t tsfb, uint32_t accumulate) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -433,7 +437,7 @@ gemm_mxfp8_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     // full: the producer's expect_tx arrive + the LEADER's four loader warps; the partner's loaders are the 16 doorbell bytes
     for (int i = 0; i < STAGES2; ++i) { mbar_init(&s.full[i], 1 + 4); mbar_init(&s.empty[i], 1); }
     mbar_init(&s.tfull, 1);
-    mbar_init(&s.tempty[0], 8); mbar_init(&s.tempty[1], 8);
+    mbar_init(&s.tempty, 8);
     s.abort = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
@@ -462,11 +466,8 @@ gemm_mxfp8_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
           const uint32_t lbar = mapa(s32(&s.full[stage]), 0);
           if (leader) mbar_expect_tx(&s.full[stage], 2 * (A_STAGE + B_STAGE) + 16);
           tma_load_3d_2sm(s.a[stage], &tmap_a, lbar, (int)(kb * BK), (int)(ar % g.a_rows_per_rec), (int)(ar / g.a_rows_per_rec));
-#pragma unroll
-          for (uint32_t h = 0; h < 2; ++h) {
-            const uint32_t br = nt * BN2 + h * 128 + rank * 64;             // 64-row boxes never straddle records (rows_per_rec % 128 == 0)
-            tma_load_3d_2sm(s.b[stage][h], &tmap_b, lbar, (int)(kb * BK), (int)(br % g.b_rows_per_rec), (int)(br / g.b_rows_per_rec));
-          }
+          const uint32_t br = nt * BN2 + rank * 128;                        // 128-row boxes never straddle records (rows_per_rec % 128 == 0)
+          tma_load_3d_2sm(s.b[stage], &tmap_b, lbar, (int)(kb * BK), (int)(br % g.b_rows_per_rec), (int)(br / g.b_rows_per_rec));
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         }
       }
@@ -478,48 +479,40 @@ gemm_mxfp8_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     if (leader && lane == 0) {
       uint32_t stage = 0, phase = 0, tphase = 0;
       auto sf_cols = [&](uint32_t st) { return tmem_base + kSfCol0_2 + st * 16; };
-      auto copy_scales = [&](uint32_t st) {                                   // SFA, SFB of half 0, SFB of half 1: in both CTAs, each from its own chunks
+      auto copy_scales = [&](uint32_t st) {                                   // SFA and the two SFB chunks: in both CTAs, each from its own shared memory
         utccp_32x128b_warpx4_2sm(sf_cols(st), smem_desc_sf(s.sfa[st]));
-        utccp_32x128b_warpx4_2sm(sf_cols(st) + 4, smem_desc_sf(s.sfb[st][0]));
-        utccp_32x128b_warpx4_2sm(sf_cols(st) + 8, smem_desc_sf(s.sfb[st][1]));
+        utccp_32x128b_warpx4_2sm(sf_cols(st) + 4, smem_desc_sf(s.sfb[st][0]));          // columns 0-127 of the tile
+        utccp_32x128b_warpx4_2sm(sf_cols(st) + 8, smem_desc_sf(s.sfb[st][1]));          // columns 128-255
       };
-      auto issue_half = [&](uint32_t st, uint32_t h, bool first) {
-        const uint64_t da = smem_desc_sw128(s.a[st]), db = smem_desc_sw128(s.b[st][h]);
-        const uint32_t tsfa = sf_cols(st), tsfb = sf_cols(st) + 4 + h * 4;
-#pragma unroll
-        for (uint32_t k = 0; k < BK / UMMA_K; ++k)
-          umma_mxf8_2sm(tmem_base + h * 128, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), mx_idesc2(k), tsfa | (k << 30), tsfb | (k << 30), !first || k != 0);
-      };
+      // where the issuer's time goes (cluster 0 reports it in out[7], as the bf16 wide kernel does): cycles waiting for
+      // operands + scale chunks / for TMEM / in the loop
+      long long w_full = 0, w_tmem = 0;
+      const long long t_loop = clock64();
       for (uint32_t tile = unit; tile < n_tiles && !s.abort; tile += n_units) {
-        const uint32_t ahead = k_blks < (uint32_t)(STAGES2 - 1) ? k_blks : (uint32_t)(STAGES2 - 1);
-        if (!mbar_wait_t(s, &s.tempty[0], tphase ^ 1)) goto mma2_done;
+        long long t0 = clock64();
+        if (!mbar_wait_t(s, &s.tempty, tphase ^ 1)) goto mma2_done;             // both CTAs' epilogues have the previous tile in registers
+        w_tmem += clock64() - t0;
         tc_fence_after();
-        uint32_t st = stage, ph = phase;
-        for (uint32_t i = 0; i < ahead; ++i) {                                 // half 0 runs ahead while half 1 is still being drained
-          if (!mbar_wait_t(s, &s.full[st], ph)) goto mma2_done;
-          tc_fence_after();
-          copy_scales(st);
-          issue_half(st, 0, i == 0);
-          if (++st == STAGES2) { st = 0; ph ^= 1; }
-        }
-        if (!mbar_wait_t(s, &s.tempty[1], tphase ^ 1)) goto mma2_done;
-        tc_fence_after();
-        for (uint32_t i = 0; i < ahead; ++i) {
-          issue_half(stage, 1, i == 0);
-          tc_commit_2sm(&s.empty[stage]);
-          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
-        }
-        for (uint32_t kb = ahead; kb < k_blks; ++kb) {
+        for (uint32_t kb = 0; kb < k_blks; ++kb) {
+          t0 = clock64();
           if (!mbar_wait_t(s, &s.full[stage], phase)) goto mma2_done;
+          w_full += clock64() - t0;
           tc_fence_after();
           copy_scales(stage);
-          issue_half(stage, 0, false);
-          issue_half(stage, 1, false);
+          const uint64_t da = smem_desc_sw128(s.a[stage]), db = smem_desc_sw128(s.b[stage]);
+          const uint32_t tsfa = sf_cols(stage), tsfb = tsfa + 4;
+#pragma unroll
+          for (uint32_t k = 0; k < BK / UMMA_K; ++k)
+            umma_mxf8_2sm(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), mx_idesc2(k), tsfa | (k << 30), tsfb | (k << 30), (kb | k) != 0);
           tc_commit_2sm(&s.empty[stage]);
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         }
         tc_commit_2sm(&s.tfull);
         tphase ^= 1;
+      }
+      if (unit == 0) {
+        const unsigned long long tot = (unsigned long long)(clock64() - t_loop);
+        g.out[7] = (((unsigned long long)w_full >> 4) & 0x1fffffull) | ((((unsigned long long)w_tmem >> 4) & 0x1fffffull) << 21) | ((tot >> 4) << 42);
       }
     }
   mma2_done:
@@ -536,41 +529,38 @@ gemm_mxfp8_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       tc_fence_after();
       const uint32_t row = (mt * 2 + rank) * BM + q * 32 + lane;
       __nv_bfloat16* crow = g.c + (size_t)row * g.N + (size_t)nt * BN2;
+      const uint32_t taddr = tmem_base + ((q * 32u) << 16);
 #pragma unroll 1
-      for (uint32_t h = 0; h < 2; ++h) {
-        const uint32_t taddr = tmem_base + ((q * 32u) << 16) + h * 128;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          tmem_ld32(taddr + c * 32, r);
-          tmem_ld_wait();
-          if (c == 3) {                                                        // the half is in registers: hand it back before storing
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if (leader) mbar_arrive(&s.tempty[h]);
-              else mbar_arrive_remote(mapa(s32(&s.tempty[h]), 0));
-            }
+      for (int c = 0; c < BN2 / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+        if (c == BN2 / 32 - 1) {                                               // the accumulator is in registers: hand it back before storing
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (leader) mbar_arrive(&s.tempty);
+            else mbar_arrive_remote(mapa(s32(&s.tempty), 0));
           }
-          const uint32_t col0 = nt * BN2 + h * 128 + c * 32;
-          if (row < g.M && col0 < g.N) {
-            __nv_bfloat16* dstp = crow + h * 128 + c * 32;
-            if (col0 + 32 <= g.N && (g.N & 7) == 0) {
-              uint4* dst = reinterpret_cast<uint4*>(dstp);
+        }
+        const uint32_t col0 = nt * BN2 + c * 32;
+        if (row < g.M && col0 < g.N) {
+          __nv_bfloat16* dstp = crow + c * 32;
+          if (col0 + 32 <= g.N && (g.N & 7) == 0) {
+            uint4* dst = reinterpret_cast<uint4*>(dstp);
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                dst[j] = make_uint4(pack_bf16(r[8 * j], r[8 * j + 1]), pack_bf16(r[8 * j + 2], r[8 * j + 3]), pack_bf16(r[8 * j + 4], r[8 * j + 5]),
-                                    pack_bf16(r[8 * j + 6], r[8 * j + 7]));
-            } else {
-              for (int j = 0; j < 32 && col0 + j < g.N; ++j) dstp[j] = __float2bfloat16_rn(__uint_as_float(r[j]));
-            }
+            for (int j = 0; j < 4; ++j)
+              dst[j] = make_uint4(pack_bf16(r[8 * j], r[8 * j + 1]), pack_bf16(r[8 * j + 2], r[8 * j + 3]), pack_bf16(r[8 * j + 4], r[8 * j + 5]),
+                                  pack_bf16(r[8 * j + 6], r[8 * j + 7]));
+          } else {
+            for (int j = 0; j < 32 && col0 + j < g.N; ++j) dstp[j] = __float2bfloat16_rn(__uint_as_float(r[j]));
           }
         }
       }
     }
   } else {
     // ===================== scale loaders (warps 6-9, both CTAs): thread (w, lane) owns row w * 32 + lane of this CTA's A rows and
-    // of each 128-column half of B
+    // of each 128-column half of the tile's B rows (every CTA needs the scales of all 256 columns)
     const uint32_t w = warp - 6;
     uint32_t stage = 0, phase = 0;
     auto ld16 = [&](const uint8_t* base, uint64_t rec_stride, uint32_t rows_per_rec, uint32_t rows, uint32_t row, uint32_t kb) -> uint4 {
@@ -709,7 +699,7 @@ RN_API int rn_k_gemm_mxfp8(uint64_t stream, int grid, uint64_t a_q, uint64_t a_s
   // cta_group: 2 = CTA-pair kernel (256 x 256 per pair), 1 = single-CTA kernel (128 x 128), 0 = pair when the matrix has more
   // than one 128-row block (a pair tile hanging over the last rows computes zeros: correct, wasted)
   if ((cta_group == 2 || (cta_group == 0 && M > BM)) && grid >= 2) {
-    rc = make_map3(&mb, (const void*)b_q, N, K, b_rows_per_rec, b_rec_stride >= 16 ? (b_rec_stride + 15) / 16 * 16 : 16, 64);
+    rc = make_map3(&mb, (const void*)b_q, N, K, b_rows_per_rec, b_rec_stride >= 16 ? (b_rec_stride + 15) / 16 * 16 : 16, 128);
     if (rc) return rc;
     const uint32_t n_tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN2 - 1) / BN2);
     grid &= ~1;

@@ -56,6 +56,8 @@ class MxResult:
     M: int
     N: int
     K: int
+    variant: int = 0                       # 1 = single-CTA kernel, 2 = CTA-pair kernel
+    issuer_cycles: dict | None = None      # pair kernel, cluster 0: cycles the MMA issuer waited for operands+scales / for TMEM / in its loop
 
     @property
     def ok(self) -> bool:
@@ -89,7 +91,11 @@ def gemm_mxfp8(ctx, a: MxOperand, b: MxOperand, c: torch.Tensor, grid: int = 0, 
         return out_view, ws
     ws.synchronize()
     w = (C.c_int64 * 8).from_buffer(out_view)
-    return MxResult(WAIT_STATUS.get(w[0], str(w[0])), w[2] - w[1], M, Nn, K)
+    r = MxResult(WAIT_STATUS.get(w[0], str(w[0])), w[2] - w[1], M, Nn, K, variant=int(w[6]))
+    u = w[7] & 0xFFFFFFFFFFFFFFFF
+    if u:
+        r.issuer_cycles = {"wait_operands": (u & 0x1FFFFF) << 4, "wait_tmem": ((u >> 21) & 0x1FFFFF) << 4, "loop": (u >> 42) << 4}
+    return r
 
 
 # ------------------------------------------------------------------ PyTorch references
