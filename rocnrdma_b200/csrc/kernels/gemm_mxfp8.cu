@@ -64,6 +64,7 @@ struct MxArgs {
   uint32_t M, N, K;
   unsigned long long* out;   // [status, t_start, t_end, tiles, 0...]: mapped pinned HOST memory -- written by the last CTA only
   unsigned int* done;        // device scratch (zeroed, self-cleaning): CTAs finished
+  uint32_t tma_store;        // pair kernel: C rows are 16-byte multiples -> epilogue through staged TMA tensor stores
 };
 // Result words live in host memory: one atomic per CTA there (the first version's atomicMax of the end time) is a PCIe
 // round trip each -- 148 of them serialised cost ~150 us per launch, more than a 4096^3 product.  Count in device memory,
@@ -354,6 +355,7 @@ struct alignas(1024) Smem2 {
   uint8_t b[STAGES2][B_STAGE];                 // this CTA's 128 of the tile's 256 B rows (leader: columns 0-127, partner: 128-255)
   alignas(128) uint8_t sfa[STAGES2][SF_STAGE];
   alignas(128) uint8_t sfb[STAGES2][2][SF_STAGE];
+  alignas(1024) uint8_t stage_c[4][4096];      // epilogue staging: per warp one 32-row x 64-column bf16 box (SWIZZLE_128B)
   alignas(16) uint8_t bell[STAGES2][16];       // landing pad of the partner's "chunks written" doorbell copy (leader only)
   alignas(8) uint64_t full[STAGES2], empty[STAGES2], tfull, tempty;
   uint32_t tmem_base;
@@ -397,6 +399,12 @@ __device__ __forceinline__ void ring_bell(uint32_t dst_cluster, const void* src_
   asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], 16, [%2];"
                ::"r"(dst_cluster), "r"(s32(src_cta)), "r"(bar_cluster) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(s32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 template <typename S>
 __device__ __forceinline__ bool mbar_wait_t(S& s, uint64_t* b, uint32_t parity) {
   if (mbar_try(b, parity)) return true;
@@ -421,7 +429,8 @@ __device__ __forceinline__ void tile_coords2(uint32_t t, uint32_t m_tiles, uint3
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-gemm_mxfp8_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ MxArgs g) {
+gemm_mxfp8_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_c,
+                       const __grid_constant__ MxArgs g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Smem2& s = *reinterpret_cast<Smem2*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -530,34 +539,55 @@ gemm_mxfp8_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       const uint32_t row = (mt * 2 + rank) * BM + q * 32 + lane;
       __nv_bfloat16* crow = g.c + (size_t)row * g.N + (size_t)nt * BN2;
       const uint32_t taddr = tmem_base + ((q * 32u) << 16);
+      auto release = [&]() {                                                   // the accumulator is in registers: hand it back before storing
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_arrive(&s.tempty);
+          else mbar_arrive_remote(mapa(s32(&s.tempty), 0));
+        }
+      };
+      if (g.tma_store) {
+        // as gemm_send.cu: bf16 rows staged in the SWIZZLE_128B pattern, one lane stores the 32 x 64 box (TMA clips at the edges).
+        // With per-thread row stores in this loop the LSU back-pressure sat between the TMEM loads: the issuer waited ~10 k
+        // cycles per tile for TMEM; staged, the drain is the TMEM read itself.
+        const uint32_t buf = s32(s.stage_c[q]), rowp = buf + lane * 128;
 #pragma unroll 1
-      for (int c = 0; c < BN2 / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
-        tmem_ld_wait();
-        if (c == BN2 / 32 - 1) {                                               // the accumulator is in registers: hand it back before storing
-          tc_fence_before();
+        for (int c = 0; c < BN2 / 64; ++c) {
+          uint32_t r[64];
+          tmem_ld32(taddr + c * 64, r);
+          tmem_ld32(taddr + c * 64 + 32, r + 32);
+          tmem_ld_wait();
+          if (c == BN2 / 64 - 1) release();
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous store has read the box
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            st_shared_v4(rowp + ((uint32_t)(j ^ (lane & 7)) << 4), pack_bf16(r[8 * j], r[8 * j + 1]), pack_bf16(r[8 * j + 2], r[8 * j + 3]),
+                         pack_bf16(r[8 * j + 4], r[8 * j + 5]), pack_bf16(r[8 * j + 6], r[8 * j + 7]));
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) {
-            if (leader) mbar_arrive(&s.tempty);
-            else mbar_arrive_remote(mapa(s32(&s.tempty), 0));
+            tma_store_2d(&tmap_c, s.stage_c[q], (int)(nt * BN2 + c * 64), (int)((mt * 2 + rank) * BM + q * 32));
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
-        const uint32_t col0 = nt * BN2 + c * 32;
-        if (row < g.M && col0 < g.N) {
-          __nv_bfloat16* dstp = crow + c * 32;
-          if (col0 + 32 <= g.N && (g.N & 7) == 0) {
-            uint4* dst = reinterpret_cast<uint4*>(dstp);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              dst[j] = make_uint4(pack_bf16(r[8 * j], r[8 * j + 1]), pack_bf16(r[8 * j + 2], r[8 * j + 3]), pack_bf16(r[8 * j + 4], r[8 * j + 5]),
-                                  pack_bf16(r[8 * j + 6], r[8 * j + 7]));
-          } else {
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BN2 / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          tmem_ld_wait();
+          if (c == BN2 / 32 - 1) release();
+          const uint32_t col0 = nt * BN2 + c * 32;
+          if (row < g.M && col0 < g.N) {
+            __nv_bfloat16* dstp = crow + c * 32;
             for (int j = 0; j < 32 && col0 + j < g.N; ++j) dstp[j] = __float2bfloat16_rn(__uint_as_float(r[j]));
           }
         }
       }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");       // staged rows have left shared memory and are written
   } else {
     // ===================== scale loaders (warps 6-9, both CTAs): thread (w, lane) owns row w * 32 + lane of this CTA's A rows and
     // of each 128-column half of the tile's B rows (every CTA needs the scales of all 256 columns)
@@ -689,7 +719,7 @@ RN_API int rn_k_gemm_mxfp8(uint64_t stream, int grid, uint64_t a_q, uint64_t a_s
   MxArgs g;
   g.a_s = (const uint8_t*)a_s; g.b_s = (const uint8_t*)b_s;
   g.a_rec_stride = a_rec_stride; g.b_rec_stride = b_rec_stride; g.a_rows_per_rec = a_rows_per_rec; g.b_rows_per_rec = b_rows_per_rec;
-  g.c = (__nv_bfloat16*)c; g.M = M; g.N = N; g.K = K;
+  g.c = (__nv_bfloat16*)c; g.M = M; g.N = N; g.K = K; g.tma_store = 0;
   g.out = (unsigned long long*)out_dev;
   g.done = (unsigned int*)done_dev;
   if (!done_dev) return -22;
@@ -701,13 +731,26 @@ RN_API int rn_k_gemm_mxfp8(uint64_t stream, int grid, uint64_t a_q, uint64_t a_s
   if ((cta_group == 2 || (cta_group == 0 && M > BM)) && grid >= 2) {
     rc = make_map3(&mb, (const void*)b_q, N, K, b_rows_per_rec, b_rec_stride >= 16 ? (b_rec_stride + 15) / 16 * 16 : 16, 128);
     if (rc) return rc;
+    CUtensorMap mc;
+    g.tma_store = (N % 8 == 0 && (c & 15) == 0) ? 1u : 0u;
+    if (g.tma_store) {
+      EncodeTiledFn fn = encode_tiled();
+      cuuint64_t dims[2] = {N, M};
+      cuuint64_t strides[1] = {(cuuint64_t)N * 2};
+      cuuint32_t box[2] = {64, 32};
+      cuuint32_t estr[2] = {1, 1};
+      if (!fn || fn(&mc, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)c, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        g.tma_store = 0;
+    }
+    if (!g.tma_store) mc = ma;                                       // never dereferenced
     const uint32_t n_tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN2 - 1) / BN2);
     grid &= ~1;
     if ((uint32_t)grid > 2 * n_tiles) grid = (int)(2 * n_tiles);
     const size_t smem = sizeof(Smem2) + 1024;
     cudaError_t e = cudaFuncSetAttribute(gemm_mxfp8_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return -(int)e - 1000;
-    gemm_mxfp8_pair_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ma, mb, g);
+    gemm_mxfp8_pair_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ma, mb, mc, g);
     return (int)cudaGetLastError();
   }
   const uint32_t n_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
