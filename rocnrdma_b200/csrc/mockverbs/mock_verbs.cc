@@ -498,15 +498,21 @@ bool nic_sweep() {
       if (!qp || (qp->v.state != IBV_QPS_RTS && qp->v.state != IBV_QPS_ERR && qp->v.state != IBV_QPS_SQD)) continue;
       // A doorbell is a store to either BlueFlame register; its value is the first 8 bytes of a ctrl segment.
       bool rung = false;
+      unsigned long long rung_val = 0;
       for (int r = 0; r < 2; ++r) {
         const unsigned long long val = __atomic_load_n((unsigned long long*)(qp->uar + kBfOffset + r * kBfSize), __ATOMIC_ACQUIRE);
-        if (val != qp->bf_seen[r]) { qp->bf_seen[r] = val; rung = true; }
+        if (val != qp->bf_seen[r]) { qp->bf_seen[r] = val; rung = true; rung_val = val; }
       }
       const uint16_t pi16 = (uint16_t)be32(*(volatile uint32_t*)&qp->dbrec[rn::DBR_SND]);
       uint16_t pending = (uint16_t)(pi16 - (uint16_t)qp->hw_sq_cons);
       if (rung) {
         qp->n_doorbells++;
-        if (pending == 0) qp->n_db_no_progress++;        // the register ran ahead of the doorbell record (ordering bug in the poster)
+        // The doorbell value is the first 8 bytes of a ctrl segment, i.e. it names a WQE index; the record, read AFTER the
+        // register, must already cover that WQE -- otherwise the register store overtook the record store (ordering bug in
+        // the poster).  ("Nothing pending" is not the test: an earlier sweep may already have executed this WQE off a
+        // record that was ahead of its doorbell, which is legal.)
+        const uint16_t bell_idx = (uint16_t)(be32((uint32_t)rung_val) >> 8);
+        if ((uint16_t)(pi16 - (uint16_t)(bell_idx + 1)) >= 0x8000u) qp->n_db_no_progress++;
       }
       // Work is only fetched on a doorbell (a real NIC does not look at the record unprompted); a WQE that had
       // to wait for a receive buffer stays pending and is retried without one.
