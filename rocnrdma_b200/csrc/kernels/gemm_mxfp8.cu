@@ -65,7 +65,31 @@ struct MxArgs {
   unsigned long long* out;   // [status, t_start, t_end, tiles, 0...]: mapped pinned HOST memory -- written by the last CTA only
   unsigned int* done;        // device scratch (zeroed, self-cleaning): CTAs finished
   uint32_t tma_store;        // pair kernel: C rows are 16-byte multiples -> epilogue through staged TMA tensor stores
+  // Receive-side fusion ("the panel arrives -> its tiles start"): one word per 128-row panel of A, nonzero once the panel's
+  // record has landed in this GPU's memory (recv_consume_kernel stamps it when the panel's receive completion shows up).
+  // nullptr: A is complete before the launch.  The TMA producer and the scale loaders wait for the word of the panel
+  // they are about to read; every wait is bounded.
+  const unsigned long long* a_ready;
+  uint64_t ready_timeout_ns;
 };
+// bounded wait for a panel's arrival word; the acquire orders it before the loads of the panel, the proxy fence extends
+// that to the async proxy (TMA reads the panel)
+__device__ __forceinline__ bool wait_panel(const unsigned long long* ready, uint32_t panel, uint64_t timeout_ns, volatile int* abort) {
+  if (!ready) return true;
+  unsigned long long v, t0 = 0;
+  for (unsigned n = 0;; ++n) {
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ready + panel) : "memory");
+    if (v) break;
+    if (*abort) return false;
+    if ((n & 63) == 63) {
+      if (!t0) t0 = globaltimer_ns();
+      else if (globaltimer_ns() - t0 > timeout_ns) { *abort = 1; return false; }
+      __nanosleep(200);
+    }
+  }
+  asm volatile("fence.proxy.async;" ::: "memory");
+  return true;
+}
 // Result words live in host memory: one atomic per CTA there (the first version's atomicMax of the end time) is a PCIe
 // round trip each -- 148 of them serialised cost ~150 us per launch, more than a 4096^3 product.  Count in device memory,
 // let the last CTA write.
@@ -202,6 +226,7 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       for (uint32_t tile = blockIdx.x; tile < n_tiles && !s.abort; tile += gridDim.x) {
         const uint32_t m_blk = tile / n_blks, n_blk = tile % n_blks;
         const uint32_t ar = m_blk * BM, br = n_blk * BN;
+        if (!wait_panel(g.a_ready, m_blk, g.ready_timeout_ns, &s.abort)) goto producer_done;
         for (uint32_t kb = 0; kb < k_blks; ++kb) {
           if (!mbar_wait(s, &s.empty[stage], phase ^ 1)) goto producer_done;
           mbar_expect_tx(&s.full[stage], A_STAGE + B_STAGE);
@@ -285,7 +310,7 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     auto ld16 = [&](const uint8_t* base, uint64_t rec_stride, uint32_t rows_per_rec, uint32_t rows, uint32_t row, uint32_t kb) -> uint4 {
       if (row < rows && kb * 4 + 16 <= ks) {
         const uint8_t* p = base + (uint64_t)(row / rows_per_rec) * rec_stride + (uint64_t)(row % rows_per_rec) * ks + (uint64_t)kb * 4;
-        if (((uintptr_t)p & 15) == 0) return __ldg(reinterpret_cast<const uint4*>(p));
+        if (((uintptr_t)p & 15) == 0) return g.a_ready ? __ldcg(reinterpret_cast<const uint4*>(p)) : __ldg(reinterpret_cast<const uint4*>(p));
       }
       return make_uint4(load_scales(base, rec_stride, rows_per_rec, rows, ks, row, kb), load_scales(base, rec_stride, rows_per_rec, rows, ks, row, kb + 1),
                         load_scales(base, rec_stride, rows_per_rec, rows, ks, row, kb + 2), load_scales(base, rec_stride, rows_per_rec, rows, ks, row, kb + 3));
@@ -293,6 +318,7 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     for (uint32_t tile = blockIdx.x; tile < n_tiles && !s.abort; tile += gridDim.x) {
       const uint32_t m_blk = tile / n_blks, n_blk = tile % n_blks;
       const uint32_t arow = m_blk * BM + w * 32 + lane, brow = n_blk * BN + w * 32 + lane;
+      if (!wait_panel(g.a_ready, m_blk, g.ready_timeout_ns, &s.abort)) goto loader_done;      // the scales travel in the same record
       uint4 ca = ld16(g.a_s, g.a_rec_stride, g.a_rows_per_rec, g.M, arow, 0), cb = ld16(g.b_s, g.b_rec_stride, g.b_rows_per_rec, g.N, brow, 0);
       for (uint32_t kb0 = 0; kb0 < k_blks; kb0 += 4) {
         uint4 na = ca, nb = cb;
@@ -470,6 +496,7 @@ gemm_mxfp8_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         uint32_t mt, nt;
         tile_coords2(tile, m_tiles, n_tiles_n, kGroup, &mt, &nt);
         const uint32_t ar = (mt * 2 + rank) * BM;
+        if (!wait_panel(g.a_ready, mt * 2 + rank, g.ready_timeout_ns, &s.abort)) goto producer2_done;   // this CTA's 128 rows are one panel
         for (uint32_t kb = 0; kb < k_blks; ++kb) {
           if (!mbar_wait_t(s, &s.empty[stage], phase ^ 1)) goto producer2_done;
           const uint32_t lbar = mapa(s32(&s.full[stage]), 0);
@@ -596,7 +623,7 @@ gemm_mxfp8_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     auto ld16 = [&](const uint8_t* base, uint64_t rec_stride, uint32_t rows_per_rec, uint32_t rows, uint32_t row, uint32_t kb) -> uint4 {
       if (row < rows && kb * 4 + 16 <= ks) {
         const uint8_t* p = base + (uint64_t)(row / rows_per_rec) * rec_stride + (uint64_t)(row % rows_per_rec) * ks + (uint64_t)kb * 4;
-        if (((uintptr_t)p & 15) == 0) return __ldg(reinterpret_cast<const uint4*>(p));
+        if (((uintptr_t)p & 15) == 0) return g.a_ready ? __ldcg(reinterpret_cast<const uint4*>(p)) : __ldg(reinterpret_cast<const uint4*>(p));
       }
       return make_uint4(load_scales(base, rec_stride, rows_per_rec, rows, ks, row, kb), load_scales(base, rec_stride, rows_per_rec, rows, ks, row, kb + 1),
                         load_scales(base, rec_stride, rows_per_rec, rows, ks, row, kb + 2), load_scales(base, rec_stride, rows_per_rec, rows, ks, row, kb + 3));
@@ -613,12 +640,19 @@ gemm_mxfp8_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     uint4 ca = make_uint4(0, 0, 0, 0), cb0 = ca, cb1 = ca;
     if (unit < n_tiles) {
       const Rows r0 = rows_of(unit);
+      if (!wait_panel(g.a_ready, r0.a / BM, g.ready_timeout_ns, &s.abort)) goto loader2_done;
       ca = ld16(g.a_s, g.a_rec_stride, g.a_rows_per_rec, g.M, r0.a, 0);
       cb0 = ld16(g.b_s, g.b_rec_stride, g.b_rows_per_rec, g.N, r0.b0, 0);
       cb1 = ld16(g.b_s, g.b_rec_stride, g.b_rows_per_rec, g.N, r0.b1, 0);
     }
     for (uint32_t tile = unit; tile < n_tiles && !s.abort; tile += n_units) {
       const Rows rw = rows_of(tile);
+      if (g.a_ready && tile != unit) {
+        if (!wait_panel(g.a_ready, rw.a / BM, g.ready_timeout_ns, &s.abort)) goto loader2_done;
+        ca = ld16(g.a_s, g.a_rec_stride, g.a_rows_per_rec, g.M, rw.a, 0);
+        cb0 = ld16(g.b_s, g.b_rec_stride, g.b_rows_per_rec, g.N, rw.b0, 0);
+        cb1 = ld16(g.b_s, g.b_rec_stride, g.b_rows_per_rec, g.N, rw.b1, 0);
+      }
       for (uint32_t kb0 = 0; kb0 < k_blks; kb0 += 4) {
         // the next group's loads are in flight while this one is handed over -- at the end of a tile that is the NEXT TILE's
         // first group (a blocking load there put ~1 us per tile on the issuer's critical path)
@@ -627,7 +661,7 @@ gemm_mxfp8_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
           na = ld16(g.a_s, g.a_rec_stride, g.a_rows_per_rec, g.M, rw.a, kb0 + 4);
           nb0 = ld16(g.b_s, g.b_rec_stride, g.b_rows_per_rec, g.N, rw.b0, kb0 + 4);
           nb1 = ld16(g.b_s, g.b_rec_stride, g.b_rows_per_rec, g.N, rw.b1, kb0 + 4);
-        } else if (tile + n_units < n_tiles) {
+        } else if (tile + n_units < n_tiles && !g.a_ready) {                  // (with arrival words the next tile's loads wait for its panel: below)
           const Rows rn = rows_of(tile + n_units);
           na = ld16(g.a_s, g.a_rec_stride, g.a_rows_per_rec, g.M, rn.a, 0);
           nb0 = ld16(g.b_s, g.b_rec_stride, g.b_rows_per_rec, g.N, rn.b0, 0);
@@ -702,7 +736,7 @@ int make_map3(CUtensorMap* m, const void* base, uint64_t rows, uint64_t K, uint6
 // plain matrix).  K % 32 == 0, K % 16 == 0 for the TMA row stride; M and N are free (bf16 C rows of N elements).
 RN_API int rn_k_gemm_mxfp8(uint64_t stream, int grid, uint64_t a_q, uint64_t a_s, uint32_t a_rows_per_rec, uint64_t a_rec_stride, uint64_t b_q,
                            uint64_t b_s, uint32_t b_rows_per_rec, uint64_t b_rec_stride, uint64_t c, uint32_t M, uint32_t N, uint32_t K,
-                           uint64_t out_dev, uint32_t cta_group, uint64_t done_dev) {
+                           uint64_t out_dev, uint32_t cta_group, uint64_t done_dev, uint64_t a_ready_dev, uint64_t ready_timeout_ms) {
   if (!M || !N || !K || (K % 32) || (K % 16)) return -22;
   if ((a_q | b_q) & 15 || (c & 1)) return -22;
   if (!a_rows_per_rec) a_rows_per_rec = M;
@@ -720,6 +754,7 @@ RN_API int rn_k_gemm_mxfp8(uint64_t stream, int grid, uint64_t a_q, uint64_t a_s
   g.a_s = (const uint8_t*)a_s; g.b_s = (const uint8_t*)b_s;
   g.a_rec_stride = a_rec_stride; g.b_rec_stride = b_rec_stride; g.a_rows_per_rec = a_rows_per_rec; g.b_rows_per_rec = b_rows_per_rec;
   g.c = (__nv_bfloat16*)c; g.M = M; g.N = N; g.K = K; g.tma_store = 0;
+  g.a_ready = (const unsigned long long*)a_ready_dev; g.ready_timeout_ns = (ready_timeout_ms ? ready_timeout_ms : 2000) * 1000000ull;
   g.out = (unsigned long long*)out_dev;
   g.done = (unsigned int*)done_dev;
   if (!done_dev) return -22;

@@ -203,7 +203,8 @@ __global__ void __launch_bounds__(32, 1) recv_consume_kernel(QpDev* qp, uint32_t
     uint32_t imm = 0;
     long long got = recv_wait(qp, &imm, timeout_ns);
     if (got < 0) { status = (int)got; break; }
-    if (stamps && imm < max_imm) stamps[imm] = globaltimer_ns();
+    // release: whoever acquires the stamp (a GEMM waiting for this panel: gemm_mxfp8.cu) also sees the panel the completion announced
+    if (stamps && imm < max_imm) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(stamps + imm), "l"(globaltimer_ns()) : "memory");
     bytes += (unsigned long long)got;
     ++seen;
   }

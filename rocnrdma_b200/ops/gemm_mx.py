@@ -69,22 +69,30 @@ class MxResult:
 
 
 def gemm_mxfp8(ctx, a: MxOperand, b: MxOperand, c: torch.Tensor, grid: int = 0, stream=None, sync: bool = True, scratch_slot: int = 3,
-               cta_group: int = 0):
+               cta_group: int = 0, a_ready=None, timeout_ms: int = 2000):
     """``c[M,N] (bf16) = dequant(a)[M,K] @ dequant(b)[N,K].T`` with the block scales applied by the tensor core.
     Any M and N; K a multiple of 32 (one MX block) and of 16 bytes.
     ``cta_group``: 2 = CTA-pair kernel (256 x 256 per pair, half the operand traffic per FLOP), 1 = single-CTA kernel
-    (128 x 128), 0 = pair for M > 128.  ``RN_MX_CTA_GROUP`` overrides (A/B switch)."""
+    (128 x 128), 0 = pair for M > 128.  ``RN_MX_CTA_GROUP`` overrides (A/B switch).
+    ``a_ready``: receive-side fusion.  An int64 tensor with one word per 128-row panel of ``a`` (``a`` living in panel or chunk
+    records of a registered receive buffer); the kernel starts a tile only once the word of the panel it reads is nonzero --
+    ``ops.recv_consume(..., stamps=a_ready)`` sets it when the panel's receive completion arrives -- so the product overlaps
+    the transfer panel by panel.  Launch with a ``grid`` that leaves SMs for whatever produces the panels (a persistent
+    kernel spinning on all SMs would starve it)."""
     import os
     if os.environ.get("RN_MX_CTA_GROUP"):
         cta_group = int(os.environ["RN_MX_CTA_GROUP"])
     M, Nn, K = a.rows, b.rows, a.K
     assert b.K == K and c.dtype == torch.bfloat16 and tuple(c.shape) == (M, Nn) and c.is_contiguous()
+    if a_ready is not None:
+        assert a_ready.dtype == torch.int64 and a_ready.numel() >= -(-M // PANEL_ROWS) and a_ready.is_cuda
     lib = N.load()
     ws = work_stream(ctx, stream)
     out_addr, out_view = ctx.scratch(64, offset=4096 + scratch_slot * 64)
     done = ctx.dev_scratch(64, offset=scratch_slot * (256 << 10))          # zeroed device counter, cleaned by the kernel
     rc = lib.rn_k_gemm_mxfp8(_stream_ptr(ws), grid, a.q_ptr, a.s_ptr, a.rows_per_rec, a.rec_stride, b.q_ptr, b.s_ptr, b.rows_per_rec,
-                             b.rec_stride, c.data_ptr(), M, Nn, K, out_addr, cta_group, done)
+                             b.rec_stride, c.data_ptr(), M, Nn, K, out_addr, cta_group, done,
+                             a_ready.data_ptr() if a_ready is not None else 0, timeout_ms)
     if rc:
         raise N.NativeError(f"gemm_mxfp8 launch failed ({rc})")
     if not sync:

@@ -108,3 +108,41 @@ def test_mxfp8_consumes_chunk_records_of_the_fused_pack(ctx):
     assert ops.gemm_mxfp8(ctx, MX.MxOperand.from_chunk_records(stg, M, K, chunk), MX.MxOperand.from_tensors(bq, bs), c).ok
     aq, as_ = MX.quantize_mx(a)
     _check(c, aq, as_, bq, bs, K)
+
+
+def test_mxfp8_starts_tiles_as_their_panels_arrive(ctx):
+    """Receive-side fusion on one GPU: GEMM 1's fp8 panels travel through the wire (RDMA_WRITE_IMM per panel), a consumer
+    kernel stamps each arrival, and GEMM 2 -- launched BEFORE anything has arrived -- starts each tile when the panel it
+    reads is there.  Everything is resident at once (engine 16 SMs, GEMM 1 on 48, consumer 1, GEMM 2 on 64)."""
+    M, K1, N1, N2 = 1024, 512, 1024, 512
+    p, q = _rand(M, K1, spread=False), _rand(N1, K1, spread=False)
+    w = _rand(N2, N1)
+    wq, ws = MX.quantize_mx(w)
+    panels = M // 128
+    nb = panels * ops.panel_record_bytes(N1)
+    snd = torch.zeros(nb, dtype=torch.uint8, device="cuda")
+    rcv = torch.zeros(nb, dtype=torch.uint8, device="cuda")
+    stamps = torch.zeros(panels, dtype=torch.int64, device="cuda")
+    y = torch.zeros(M, N2, device="cuda", dtype=torch.bfloat16)
+    sm, rm = ctx.reg_mr(snd), ctx.reg_mr(rcv)
+    qp = ctx.loopback_qp(depth=64)
+    for _ in range(panels):
+        qp.post_recv(rm, 0)
+    _, s_recv, s_mm = ctx.streams(3)          # GEMM 1 itself runs on ctx.stream (streams[0])
+    torch.cuda.synchronize()
+    ctx.engine_start(ctas=16, idle_timeout_ms=5000)
+    try:
+        view, _ = ops.recv_consume(qp, panels, panels, stamps, timeout_ms=5000, sync=False, stream=s_recv)
+        out2, _ = ops.gemm_mxfp8(ctx, MX.MxOperand.from_panel_records(rcv, M, N1), MX.MxOperand.from_tensors(wq, ws), y, grid=64,
+                                 a_ready=stamps, timeout_ms=5000, sync=False, stream=s_mm)
+        r1 = ops.gemm_send(ctx, p, q, snd, c_mr=sm, qp=qp, dst_mr=rm, out_fp8=True, with_imm=True, grid=48, timeout_ms=5000)
+        s_recv.synchronize(); s_mm.synchronize()
+    finally:
+        ctx.engine_stop()
+    assert r1.ok and r1.panels_posted == panels
+    assert ops.parse_recv(view)["seen"] == panels
+    assert torch.all(stamps != 0)
+    assert torch.equal(snd, rcv)
+    xq = rcv.reshape(panels, -1)[:, :128 * N1].reshape(M, N1)
+    xs = rcv.reshape(panels, -1)[:, 128 * N1:].reshape(M, N1 // 32)
+    _check(y, xq, xs, wq, ws, N1)
