@@ -443,6 +443,14 @@ def main():
                         "engine_ctas": r4.engine_ctas,
                         "limiter": ("NVLink store burstiness: all GEMM CTAs reach their epilogue together (~450 GB/s of SM-issued stores)"
                                     if r4.mode == "direct" else "the 32 SMs the engine takes from the GEMM")}
+                # the same wire fused into BOTH GEMMs: GPU0's epilogue sends fp8 panel records, GPU1's block-scaled GEMM starts tiles on arrival
+                ch = SG.run_chain(8192, 8192, 2048, 8192, gpus=(local_rank, local_rank + 1), reps=3)
+                res["chain_8192x8192x2048_then_x8192"] = {
+                    "ok": bool(ch["verified"]), "fused_us": round(ch["fused_us"], 1) if ch["fused_us"] else None,
+                    "sequential_us": round(ch["sequential_us"], 1) if ch["sequential_us"] else None,
+                    "fused_speedup": round(ch["speedup"], 3) if ch["speedup"] else None, "wire_bytes": ch["wire_bytes"],
+                    "timing": "host wall clock, launch to completion on both GPUs (no common device clock), best of 3",
+                    "what": ch["what"], "limiter": "GEMM 2 cannot finish before GEMM 1's last panel arrives; GEMM 1 runs on 116 SMs next to the engine"}
                 extras["config4_gemm_send_recv_nvlink"] = res
             except Exception as e:
                 extras["config4_gemm_send_recv_nvlink"] = {"error": str(e)[:200]}

@@ -68,3 +68,13 @@ def test_config4_direct_mode_epilogue_stores_over_nvlink():
     assert res.ok, res
     assert res.verified
     assert res.consumer["seen"] == 8 and res.consumer["bytes"] == 0      # zero-length signals
+
+
+def test_chained_gemms_with_the_wire_fused_into_both():
+    """GPU0's GEMM sends fp8 panel records panel by panel; GPU1's block-scaled GEMM multiplies them where they land and
+    starts each tile when its panel has arrived.  Both schedules (fused, one-after-the-other) must give the same,
+    verified, result."""
+    _need2()
+    from rocnrdma_b200.models import sendrecv_gemm as SG
+    r = SG.run_chain(2048, 1024, 512, 1024, reps=1)
+    assert r["verified"] and r["fused_us"] and r["sequential_us"], r

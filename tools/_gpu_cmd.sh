@@ -1,1 +1,2 @@
-timeout 600 python -m pytest tests/test_gemm_mx.py -m gpu -q -x -p no:cacheprovider 2>&1 | tail -15
+mkdir -p gpurun_out
+for sh in "8192 8192 2048 chain 8192" "4096 4096 4096 chain 4096" "8192 4096 4096 chain 4096"; do timeout 300 python -m rocnrdma_b200.models.sendrecv_gemm $sh 2>&1 | tail -1 | tee -a gpurun_out/chain.jsonl; done
