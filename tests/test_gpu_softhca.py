@@ -358,3 +358,131 @@ def test_ops_without_engine_are_ordered_after_the_default_stream(ctx):
     r = ops.gemm_send(ctx, a, b, c)
     assert r.ok
     assert torch.allclose(c.float(), a.float() @ b.float().T, rtol=2e-2, atol=0.5)
+
+
+# ---------------------------------------------------------------- regression tests for the round-1 review findings
+def test_counters_report_the_qp_state(ctx):
+    """rn_qp_query used to leave `state` unwritten (the assignment sat behind a // comment): counters() said RESET for every QP."""
+    src, dst = _bufs(4096)
+    ms, md = ctx.reg_mr(src), ctx.reg_mr(dst)
+    qp = ctx.loopback_qp(depth=16, mem=W.MEM_HOST_PINNED)
+    assert qp.state == "RTS" and qp.counters()["state"] == "RTS"
+    ctx.engine_start(ctas=4, idle_timeout_ms=3000)
+    try:
+        qp.post_raw(W.OP_RDMA_WRITE, ms.addr, ms.lkey, md.addr, 0xdead, 64)           # bad rkey -> error CQE -> QP in ERR
+        wc = qp.scq.wait(1)[0]
+    finally:
+        ctx.engine_stop()
+    assert wc.is_error
+    assert qp.state == "ERR" and qp.counters()["state"] == "ERR"
+
+
+def test_host_post_beyond_the_queue_depth_is_refused(ctx):
+    """No flow control used to mean: the (depth + 1)-th post overwrote an unexecuted WQE.  Now it is ENOMEM, as ibv_post_send,
+    and polling completions frees the slots again."""
+    src, dst = _bufs(1 << 16)
+    ms, md = ctx.reg_mr(src), ctx.reg_mr(dst)
+    qp = ctx.loopback_qp(depth=8, mem=W.MEM_HOST_PINNED)
+    for i in range(8):                                                                  # no engine yet: nothing completes
+        qp.post_write(ms, md, 4096, src_off=i * 4096, dst_off=i * 4096)
+    with pytest.raises(rn._native.NativeError) as e:
+        qp.post_write(ms, md, 4096)
+    assert "-12" in str(e.value) or "ENOMEM" in str(e.value)
+    ctx.engine_start(ctas=4, idle_timeout_ms=3000)
+    try:
+        assert len(qp.scq.wait(8)) == 8
+        for i in range(8):                                                              # a full window fits again
+            qp.post_write(ms, md, 4096, src_off=(8 + i) * 4096, dst_off=(8 + i) * 4096)
+        assert len(qp.scq.wait(8)) == 8
+    finally:
+        ctx.engine_stop()
+    assert torch.equal(src, dst) and qp.counters()["n_err"] == 0
+    rq = ctx.loopback_qp(depth=4, mem=W.MEM_HOST_PINNED)
+    for _ in range(4):
+        rq.post_recv(md, 64)
+    with pytest.raises(rn._native.NativeError):
+        rq.post_recv(md, 64)                                                            # the receive queue has a depth too
+
+
+def test_unpolled_cq_overruns_instead_of_wrapping(ctx):
+    """The engine used to reserve CQ slots without looking at the consumer index: an unpolled CQ wrapped over valid CQEs.
+    Now the completion that would not fit raises a CQ overrun and the QP goes to ERR."""
+    src, dst = _bufs(4096)
+    ms, md = ctx.reg_mr(src), ctx.reg_mr(dst)
+    cq = ctx.create_cq(4, W.MEM_HOST_PINNED)
+    qp = ctx.create_qp(cq, cq, 32, 4, W.MEM_HOST_PINNED).connect()
+    ctx.engine_start(ctas=4, idle_timeout_ms=3000)
+    try:
+        for _ in range(12):                                                             # 12 signalled writes, nobody polls a 4-entry CQ
+            qp.post_write(ms, md, 64)
+        import time
+        t0 = time.time()
+        while qp.state != "ERR" and time.time() - t0 < 3:
+            time.sleep(0.01)
+    finally:
+        ctx.engine_stop()
+    assert qp.state == "ERR"
+    good = [w for w in cq.poll(16) if not w.is_error]
+    assert len(good) <= 4                                                               # what is there is intact: never more than the ring holds
+
+
+def test_shared_send_and_receive_cq_with_write_imm(ctx):
+    """cq_poll_once used to take every CQE for a send completion of its QP.  With one CQ for both directions a receive
+    completion (WRITE_IMM) was swallowed and its wqe_counter was applied to sq_cons.  The device poster must only consume
+    its own requester CQEs; the receive side gets its arrivals."""
+    chunk = 1 << 16
+    x = torch.randn(1 << 19, device="cuda:0").to(torch.bfloat16)
+    nb = ops.staging_bytes(x.numel(), chunk)
+    stg = torch.zeros(nb, dtype=torch.uint8, device="cuda:0")
+    rem = torch.zeros(nb, dtype=torch.uint8, device="cuda:0")
+    y = torch.zeros_like(x)
+    smr, rmr = ctx.reg_mr(stg), ctx.reg_mr(rem)
+    qp = ctx.loopback_qp(depth=64, shared_cq=True)
+    n_rec = x.numel() // chunk
+    for _ in range(n_rec):
+        qp.post_recv(rmr, 0)
+    _, s_rx = ctx.streams(2)
+    torch.cuda.synchronize()
+    ctx.engine_start(ctas=8, idle_timeout_ms=3000)
+    try:
+        # receiver first (it waits on the shared CQ from the device), then the poster: each must leave the other's CQEs alone
+        view, _ = ops.unpack_fp8(ctx, rem, y, chunk_elems=chunk, qp=qp, timeout_ms=4000, sync=False, stream=s_rx)
+        pr = ops.pack_fp8_write(ctx, x, smr, qp=qp, dst_mr=rmr, chunk_elems=chunk, with_imm=True, signal_every=1, timeout_ms=4000)
+        s_rx.synchronize()
+    finally:
+        ctx.engine_stop()
+    assert pr.ok, pr.status
+    assert torch.equal(rem, ops.ref_pack_fp8(x, chunk))
+    assert torch.equal(y, ops.ref_unpack_fp8(rem, x.numel(), chunk))
+    c = qp.counters()
+    assert c["n_err"] == 0 and c["sq_cons"] <= c["resv_head"]
+
+
+def test_reset_forgets_stale_ready_flags_and_wqes(ctx):
+    """RESET rewound the indices but kept ready_flags[] and the old WQE bytes: after reuse the shared submit rang the doorbell
+    over unwritten slots and the engine re-executed stale descriptors.  Post a few through the shared path, reset, reconnect,
+    post fewer: exactly the new ones execute."""
+    src, dst = _bufs(1 << 16)
+    ms, md = ctx.reg_mr(src), ctx.reg_mr(dst)
+    qp = ctx.loopback_qp(depth=64)
+    torch.cuda.synchronize()
+    ctx.engine_start(ctas=8, idle_timeout_ms=3000)
+    try:
+        r = ops.shared_post_stress(qp, ms, md, ctas=4, per_cta=6)                       # 24 WQEs through sq_submit_shared
+        assert r["status"] == "OK" and r["posted"] == 24
+    finally:
+        ctx.engine_stop()
+    qp.modify(W.QPS_RESET)
+    qp.connect()
+    assert qp.state == "RTS"
+    dst.zero_()
+    torch.cuda.synchronize()
+    ctx.engine_start(ctas=8, idle_timeout_ms=3000)
+    try:
+        r = ops.shared_post_stress(qp, ms, md, ctas=2, per_cta=3)                       # 6 WQEs: slots 6..23 still hold the old bytes
+        assert r["status"] == "OK" and r["posted"] == 6
+    finally:
+        ctx.engine_stop()
+    c = qp.counters()
+    # 6 writes + the kernel's flush NOP; a stale slot executed again would show as more WQEs (and as bytes in dst)
+    assert c["n_wqe"] == 7 and c["n_err"] == 0 and c["retire_head"] == 7, c
