@@ -367,19 +367,22 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 //   * TMEM: one 256-column accumulator (single-buffered: 512 columns do not hold two of them plus the scale factors).
 //     The epilogue releases it the moment its last values are in registers; what stays exposed is the TMEM drain
 //     (~1.5 k cycles per tile, see gemm_send.cu).
-//   * Scale factors: tcgen05.cp.cta_group::2 is issued by the leader and copies, in EACH CTA, that CTA's own chunk into
-//     its own TMEM (operand descriptors of a pair instruction are CTA-relative).  Both CTAs therefore build chunks: A
-//     scales for their own 128 rows, B scales for all 256 columns (two chunks, adjacent 4-column groups in TMEM).  The
-//     partner's chunks must be complete before the leader issues the copies: its four loader warps meet at a named
-//     barrier and one thread rings a 16-byte shared::cta -> shared::cluster bulk copy whose completion is counted on the
-//     LEADER's full barrier -- a hardware signal, no release-scoped remote arrive on anybody's critical path (that
-//     pattern halved the bf16 pair kernel once).
+//   * Scale factors are written into TMEM by the LOADER warps (tcgen05.st), not copied by the tensor pipe: each CTA needs
+//     the A scales of its own 128 rows and the B scales of all 256 columns (three 128-row chunks = 4 TMEM columns each,
+//     replicated in the four lane quarters).  The four loader warps exchange their rows' words through shared memory and
+//     each writes the complete chunks into the lane quarter it may access.  (The first version staged chunks in shared
+//     memory and had the issuer copy them with tcgen05.cp.cta_group::2 -- which does copy, in each CTA, that CTA's own
+//     chunk into its own TMEM -- but the copies execute in the tensor pipe, in order with the MMAs: ~48 cycles each, three
+//     per k-block, 144 of the 730 cycles a k-block took.)  The partner's TMEM must be ready before the leader issues: its
+//     loader warps meet at a named barrier and one thread rings a 16-byte shared::cta -> shared::cluster bulk copy whose
+//     completion is counted on the LEADER's full barrier -- a hardware signal, no release-scoped remote arrive on
+//     anybody's critical path (that pattern halved the bf16 pair kernel once).
 constexpr int STAGES2 = 6;
 constexpr int BN2 = 256;
 struct alignas(1024) Smem2 {
   uint8_t a[STAGES2][A_STAGE];                 // this CTA's 128 rows of A
   uint8_t b[STAGES2][B_STAGE];                 // this CTA's 128 of the tile's 256 B rows (leader: columns 0-127, partner: 128-255)
-  alignas(128) uint8_t sfa[STAGES2][SF_STAGE];
+  alignas(128) uint8_t sfa[STAGES2][SF_STAGE];   // scale words: exchange buffers of the loader warps (chunk layout), per stage
   alignas(128) uint8_t sfb[STAGES2][2][SF_STAGE];
   alignas(1024) uint8_t stage_c[4][4096];      // epilogue staging: per warp one 32-row x 64-column bf16 box (SWIZZLE_128B)
   alignas(16) uint8_t bell[STAGES2][16];       // landing pad of the partner's "chunks written" doorbell copy (leader only)
@@ -409,9 +412,6 @@ __device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(s32(bar)), "h"((uint16_t)3) : "memory");
 }
-__device__ __forceinline__ void utccp_32x128b_warpx4_2sm(uint32_t tmem_dst, uint64_t sdesc) {
-  asm volatile("tcgen05.cp.cta_group::2.32x128b.warpx4 [%0], %1;" ::"r"(tmem_dst), "l"(sdesc) : "memory");
-}
 __device__ __forceinline__ uint32_t mx_idesc2(uint32_t sf_id) {    // M = 256 (both CTAs), N = 256
   return (sf_id << 4) | ((uint32_t)(256 >> 3) << 17) | (1u << 23) | ((uint32_t)(256 >> 4) << 24) | (sf_id << 29);
 }
@@ -430,6 +430,9 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint4 v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 template <typename S>
 __device__ __forceinline__ bool mbar_wait_t(S& s, uint64_t* b, uint32_t parity) {
@@ -515,11 +518,6 @@ gemm_mxfp8_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     if (leader && lane == 0) {
       uint32_t stage = 0, phase = 0, tphase = 0;
       auto sf_cols = [&](uint32_t st) { return tmem_base + kSfCol0_2 + st * 16; };
-      auto copy_scales = [&](uint32_t st) {                                   // SFA and the two SFB chunks: in both CTAs, each from its own shared memory
-        utccp_32x128b_warpx4_2sm(sf_cols(st), smem_desc_sf(s.sfa[st]));
-        utccp_32x128b_warpx4_2sm(sf_cols(st) + 4, smem_desc_sf(s.sfb[st][0]));          // columns 0-127 of the tile
-        utccp_32x128b_warpx4_2sm(sf_cols(st) + 8, smem_desc_sf(s.sfb[st][1]));          // columns 128-255
-      };
       // where the issuer's time goes (cluster 0 reports it in out[7], as the bf16 wide kernel does): cycles waiting for
       // operands + scale chunks / for TMEM / in the loop
       long long w_full = 0, w_tmem = 0;
@@ -534,8 +532,7 @@ gemm_mxfp8_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
           if (!mbar_wait_t(s, &s.full[stage], phase)) goto mma2_done;
           w_full += clock64() - t0;
           tc_fence_after();
-          copy_scales(stage);
-          const uint64_t da = smem_desc_sw128(s.a[stage]), db = smem_desc_sw128(s.b[stage]);
+          const uint64_t da = smem_desc_sw128(s.a[stage]), db = smem_desc_sw128(s.b[stage]);   // the stage's scale factors are already in TMEM (loaders)
           const uint32_t tsfa = sf_cols(stage), tsfb = tsfa + 4;
 #pragma unroll
           for (uint32_t k = 0; k < BK / UMMA_K; ++k)
@@ -629,6 +626,7 @@ gemm_mxfp8_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                         load_scales(base, rec_stride, rows_per_rec, rows, ks, row, kb + 2), load_scales(base, rec_stride, rows_per_rec, rows, ks, row, kb + 3));
     };
     const uint32_t bell_dst = mapa(s32(&s.bell[0][0]), 0);
+    const uint32_t tq = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16);     // the TMEM lane quarter this warp may write
     // rows this thread serves for a tile, and the first group (k-blocks 0-3) of their scales
     struct Rows { uint32_t a, b0, b1; };
     auto rows_of = [&](uint32_t tile) -> Rows {
@@ -675,12 +673,23 @@ gemm_mxfp8_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
           *reinterpret_cast<uint32_t*>(&s.sfa[stage][lane * 16 + w * 4]) = wa[j];
           *reinterpret_cast<uint32_t*>(&s.sfb[stage][0][lane * 16 + w * 4]) = wb0[j];
           *reinterpret_cast<uint32_t*>(&s.sfb[stage][1][lane * 16 + w * 4]) = wb1[j];
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");         // generic-proxy writes -> visible to tcgen05.cp
+          asm volatile("bar.sync 2, 128;" ::: "memory");                      // the four warps' words of every chunk are in the exchange buffer
+          {
+            // chunk row `lane` = the scale words of tile rows lane, lane + 32, lane + 64, lane + 96: four TMEM columns of lane
+            // `lane` in every lane quarter; this warp writes the quarter it may access
+            const uint4 va = *reinterpret_cast<const uint4*>(&s.sfa[stage][lane * 16]);
+            const uint4 vb0 = *reinterpret_cast<const uint4*>(&s.sfb[stage][0][lane * 16]);
+            const uint4 vb1 = *reinterpret_cast<const uint4*>(&s.sfb[stage][1][lane * 16]);
+            const uint32_t t = tq + kSfCol0_2 + stage * 16;
+            tmem_st4(t, va); tmem_st4(t + 4, vb0); tmem_st4(t + 8, vb1);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+          }
           if (leader) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&s.full[stage]);
           } else {
-            asm volatile("bar.sync 2, 128;" ::: "memory");                    // all four loader warps of this CTA have written and fenced
+            asm volatile("bar.sync 3, 128;" ::: "memory");                    // all four lane quarters of this CTA's TMEM hold the stage's scales
             if (threadIdx.x == 6 * 32) ring_bell(bell_dst + stage * 16, s.sfa[stage], mapa(s32(&s.full[stage]), 0));
           }
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }

@@ -18,7 +18,7 @@ python - <<'PY'
 import json
 s = json.load(open("profiles/sass/summary.json"))
 need = {"gemm_send2_kernel": ["UTCHMMA.2CTA", "UTMALDG.2D.2CTA", "UTMASTG.2D"], "gemm_send3_kernel": ["UTCHMMA.2CTA", "UTMASTG.2D"],
-        "gemm_send_kernel": ["UTCHMMA", "UTMALDG.2D"], "gemm_mxfp8_pair_kernel": ["UTCQMMA.2CTA", "UTCCP.T.S.2CTA.4", "UTMALDG.3D.2CTA"],
+        "gemm_send_kernel": ["UTCHMMA", "UTMALDG.2D"], "gemm_mxfp8_pair_kernel": ["UTCQMMA.2CTA", "STTM", "UTMALDG.3D.2CTA", "UTMASTG.2D"],
         "gemm_mxfp8_kernel": ["UTCQMMA", "UTCCP.T.S.4"], "engine_kernel": ["UBLKCP.S.G"]}
 for k, ops in need.items():
     have = s[k]["blackwell"]

@@ -21,7 +21,7 @@ for m in re.finditer(r"\t\tFunction : (\S+)\n(.*?)(?=\n\t\tFunction : |\Z)", txt
         if mm:
             ops[mm.group(1)] += 1
             full[mm.group(1) + mm.group(2)] += 1
-    blackwell = {k: v for k, v in full.items() if k.split(".")[0] in ("UTCHMMA", "UTMALDG", "UTMASTG", "UTCBAR", "LDTM", "UTCATOMSWS", "UBLKCP", "SYNCS", "UTMACMDFLUSH", "F2FP", "UTCQMMA", "UTCCP")}
+    blackwell = {k: v for k, v in full.items() if k.split(".")[0] in ("UTCHMMA", "UTMALDG", "UTMASTG", "UTCBAR", "LDTM", "UTCATOMSWS", "UBLKCP", "SYNCS", "UTMACMDFLUSH", "F2FP", "UTCQMMA", "UTCCP", "STTM")}
     summary[name] = {"mangled": mangled, "instructions": sum(ops.values()), "blackwell": dict(sorted(blackwell.items())), "mnemonics": dict(ops.most_common())}
 json.dump(summary, open(os.path.join(out, "summary.json"), "w"), indent=1)
 for k, v in summary.items():
