@@ -56,6 +56,9 @@ struct PackArgs {
   uint32_t post_only;        // 1: post everything (incl. the flush) but do not wait for the wire to drain -- for profilers that
                              //    serialise kernels (the NIC / engine cannot run while this kernel is resident) and for callers
                              //    that overlap the drain with other work and reap the flush CQE later
+  uint32_t direct;           // 1: `staging` IS the peer's registered buffer (NVLink-mapped): the pack's own coalesced stores are the
+                             //    transfer; each finished record is announced by a zero-length RDMA_WRITE_IMM posted after a cumulative
+                             //    system-scope fence (as gemm_send.cu's direct mode; no engine / NIC moves the payload)
   uint32_t signal_every;     // CQE every k-th chunk (the last one is always signaled)
   unsigned int* counters;    // [0..n_chunks): tiles done per chunk ; [n_chunks]: CTAs done
   unsigned long long* acc;   // device accumulators: [0] max WQE index+1, [1] WQEs posted, [2] ~first post time
@@ -135,14 +138,14 @@ __global__ void __launch_bounds__(kPackThreads) pack_fp8_write_kernel(PackArgs a
       if (old + 1 == groups_per_chunk) {
         // acquire every other group's bytes; fences are cumulative, so on a NIC-facing QP one
         // system-scope fence here covers the whole record without a sys fence per group
-        fence_scope(sys);
+        fence_scope(sys || a.direct);
         unsigned long long idx = sq_reserve(a.qp, 1, a.timeout_ns);
         // Chunks are posted by whichever CTA finishes them, so WQE order != chunk order:
         // signal by WQE index (every k-th slot) so the CQ keeps freeing the send queue.
         const bool sig = a.signal_every <= 1 || ((idx + 1) % a.signal_every == 0);
         if (idx != ~0ull) {
           write_rdma_wqe(a.qp, idx, a.with_imm ? OP_RDMA_WRITE_IMM : OP_RDMA_WRITE, a.staging_va + (uint64_t)chunk * rec,
-                         a.lkey, a.remote_va + (uint64_t)chunk * rec, a.rkey, (uint32_t)rec,
+                         a.lkey, a.remote_va + (uint64_t)chunk * rec, a.rkey, a.direct ? 0u : (uint32_t)rec,
                          sig ? CTRL_CQ_UPDATE : 0, chunk);
           if (sq_submit(a.qp, idx, 1, a.timeout_ns, /*shared=*/true) == WAIT_OK) {
             atomicMax(&a.acc[0], idx + 1);
@@ -290,7 +293,7 @@ RN_API int rn_k_pack_fp8_write(uint64_t stream, int grid, uint64_t src, uint64_t
   PackArgs a;
   a.src = (const __nv_bfloat16*)src; a.staging = (uint8_t*)staging; a.n_elems = n_elems; a.chunk_elems = chunk_elems;
   a.n_chunks = (uint32_t)(n_elems / chunk_elems); a.qp = (QpDev*)qp_dev; a.staging_va = staging_va; a.lkey = lkey;
-  a.rkey = rkey; a.remote_va = remote_va; a.with_imm = with_imm & 1u; a.post_only = (with_imm >> 1) & 1u; a.signal_every = signal_every ? signal_every : 1;
+  a.rkey = rkey; a.remote_va = remote_va; a.with_imm = with_imm & 1u; a.post_only = (with_imm >> 1) & 1u; a.direct = (with_imm >> 2) & 1u; a.signal_every = signal_every ? signal_every : 1;
   a.counters = (unsigned int*)counters_dev;
   a.acc = (unsigned long long*)(counters_dev + (((uint64_t)a.n_chunks + 1) * 4 + 7) / 8 * 8);
   a.out = (unsigned long long*)out_dev;

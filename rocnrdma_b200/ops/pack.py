@@ -60,9 +60,13 @@ def _parse(view, n_elems, wire) -> PackResult:
 
 def pack_fp8_write(ctx, src: torch.Tensor, staging_mr, qp=None, dst_mr=None, chunk_elems: int = 1 << 20,
                    with_imm: bool = False, signal_every: int = 1, grid: int = 0, timeout_ms: int = 2000,
-                   stream=None, sync: bool = True, scratch_slot: int = 0, post_only: bool = False):
+                   stream=None, sync: bool = True, scratch_slot: int = 0, post_only: bool = False, direct: bool = False):
     """Pack ``src`` (bf16) into fp8 chunk records in ``staging_mr`` and, if ``qp`` is given,
-    RDMA-write every record to the same offset of ``dst_mr`` from inside the kernel."""
+    RDMA-write every record to the same offset of ``dst_mr`` from inside the kernel.
+    ``direct``: ``staging_mr`` is the *peer's* buffer registered with this context (NVLink-mapped, ``ctx.reg_mr(tensor_on_the_peer)``):
+    the kernel's own stores deliver the records and each one is announced by a zero-length RDMA_WRITE_IMM (needs ``with_imm``)."""
+    if direct and not (with_imm and qp is not None and dst_mr is not None):
+        raise ValueError("direct mode announces records with RDMA_WRITE_IMM: pass qp, dst_mr and with_imm=True")
     assert src.dtype == torch.bfloat16 and src.is_contiguous()
     n = src.numel()
     if n % TILE_ELEMS or chunk_elems % TILE_ELEMS or n % chunk_elems:
@@ -78,7 +82,7 @@ def pack_fp8_write(ctx, src: torch.Tensor, staging_mr, qp=None, dst_mr=None, chu
     rc = lib.rn_k_pack_fp8_write(_stream_ptr(ws), grid, src.data_ptr(), staging_mr.addr, n, chunk_elems,
                                  qp.dev_ptr if qp is not None else 0, staging_mr.addr, staging_mr.lkey,
                                  dst_mr.addr if dst_mr is not None else 0, dst_mr.rkey if dst_mr is not None else 0,
-                                 int(with_imm) | (2 if post_only else 0), signal_every, counters, out_addr, timeout_ms)
+                                 int(with_imm) | (2 if post_only else 0) | (4 if direct else 0), signal_every, counters, out_addr, timeout_ms)
     if rc:
         raise N.NativeError(f"pack_fp8_write launch failed ({rc})")
     if not sync:
@@ -108,6 +112,11 @@ def unpack_fp8(ctx, staging: torch.Tensor, dst: torch.Tensor, chunk_elems: int =
         return out_view, ws
     ws.synchronize()
     w = (C.c_int64 * 8).from_buffer(out_view)
+    return parse_unpack(out_view)
+
+
+def parse_unpack(view) -> dict:
+    w = (C.c_int64 * 8).from_buffer(view)
     return dict(status=WAIT_STATUS.get(w[0], str(w[0])), device_ns=w[2] - w[1], records_seen=w[3])
 
 

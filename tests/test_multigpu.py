@@ -78,3 +78,14 @@ def test_chained_gemms_with_the_wire_fused_into_both():
     from rocnrdma_b200.models import sendrecv_gemm as SG
     r = SG.run_chain(2048, 1024, 512, 1024, reps=1)
     assert r["verified"] and r["fused_us"] and r["sequential_us"], r
+
+
+@pytest.mark.parametrize("mode", ["engine", "direct"])
+def test_pack_on_gpu0_unpack_on_gpu1(mode):
+    """K3 -> NVLink -> K5 with no host step between: the peer's unpack kernel waits on its receive CQ from the device.
+    engine: records staged locally, moved by the DMA engine; direct: the pack kernel stores into the peer's registered
+    buffer itself and only announces each record through the queue pair."""
+    _need2()
+    from rocnrdma_b200.models import sendrecv_pack as SP
+    r = SP.run(1 << 24, 1 << 20, mode=mode, reps=1)
+    assert r["verified"] and r["fused_us"] and r["sequential_us"], r
