@@ -213,22 +213,40 @@ __global__ void __launch_bounds__(kPackThreads) unpack_fp8_kernel(UnpackArgs a) 
   const uint32_t tiles_per_chunk = a.chunk_elems / kTileElems;
   const uint64_t rec = record_bytes(a.chunk_elems);
   __shared__ int ok;
-  // chunk-major so that every CTA works on the oldest record not yet unpacked
+  // With a QP, CTA 0 is the receive-CQ poller and nothing else: it turns every RDMA_WRITE_IMM completion into an arrival flag.
+  // (The first version let every CTA poll the CQ for "its" record: hundreds of pollers contending for one consumer index made
+  // the consumer, not the wire, the tail of the pack -> NVLink -> unpack chain.)  The other CTAs unpack, chunk-major, so that
+  // every worker is on the oldest record not yet unpacked, and wait on the flag of the record they are about to read.
+  const bool polled = a.qp != nullptr;
+  unsigned int* abort_flag = a.arrived + a.n_chunks + 2;
+  if (polled && blockIdx.x == 0) {
+    if (threadIdx.x == 0) {
+      const unsigned long long t0 = globaltimer_ns();
+      uint32_t seen = 0;
+      while (seen < a.n_chunks) {
+        uint32_t imm = 0;
+        long long got = recv_wait(a.qp, &imm, 2000);
+        if (got >= 0 && imm < a.n_chunks) {
+          fence_gpu();                                        // the record (ordered before its completion) before the flag
+          atomicExch(&a.arrived[imm], 1u);
+          ++seen;
+        } else if (got == WAIT_CQE_ERROR) {
+          a.out[0] = (unsigned long long)(long long)WAIT_CQE_ERROR; atomicExch(abort_flag, 1u); break;
+        }
+        if (globaltimer_ns() - t0 > a.timeout_ns) { a.out[0] = (unsigned long long)(long long)WAIT_TIMEOUT; atomicExch(abort_flag, 1u); break; }
+      }
+      atomicAdd(&a.arrived[a.n_chunks + 1], seen);
+    }
+  } else {
+  const uint32_t first = polled ? blockIdx.x - 1 : blockIdx.x, stride = polled ? gridDim.x - 1 : gridDim.x;
   for (uint32_t chunk = 0; chunk < a.n_chunks; ++chunk) {
-    if (a.qp != nullptr) {
+    if (polled) {
+      if (first >= tiles_per_chunk) break;                    // this CTA never has a tile
       if (threadIdx.x == 0) {
         ok = 1;
-        unsigned long long t0 = globaltimer_ns();
-        while (*(volatile unsigned int*)&a.arrived[chunk] == 0) {
-          uint32_t imm = 0;
-          long long got = recv_wait(a.qp, &imm, 2000);     // short poll: others may consume "our" CQE
-          if (got >= 0 && imm < a.n_chunks) {
-            atomicExch(&a.arrived[imm], 1u);
-            atomicAdd(&a.arrived[a.n_chunks + 1], 1u);
-          } else if (got == WAIT_CQE_ERROR) {
-            a.out[0] = (unsigned long long)(long long)WAIT_CQE_ERROR; ok = 0; break;
-          }
-          if (globaltimer_ns() - t0 > a.timeout_ns) { a.out[0] = (unsigned long long)(long long)WAIT_TIMEOUT; ok = 0; break; }
+        for (unsigned n = 0; *(volatile unsigned int*)&a.arrived[chunk] == 0; ++n) {
+          if (*(volatile unsigned int*)abort_flag) { ok = 0; break; }
+          __nanosleep(n < 64 ? 50 : 400);
         }
         fence_gpu();
       }
@@ -238,7 +256,7 @@ __global__ void __launch_bounds__(kPackThreads) unpack_fp8_kernel(UnpackArgs a) 
       if (!good) break;
     }
     const uint8_t* recp = a.staging + (uint64_t)chunk * rec;
-    for (uint32_t t = blockIdx.x; t < tiles_per_chunk; t += gridDim.x) {
+    for (uint32_t t = first; t < tiles_per_chunk; t += stride) {
       const uint4* in = reinterpret_cast<const uint4*>(recp + (uint64_t)t * kTileElems + (uint64_t)threadIdx.x * kBlockElems);
       uint4 q0 = in[0], q1 = in[1];
       const int e = (int)recp[a.chunk_elems + (uint64_t)t * kPackThreads + threadIdx.x] - 127;
@@ -264,15 +282,17 @@ __global__ void __launch_bounds__(kPackThreads) unpack_fp8_kernel(UnpackArgs a) 
       dst[3] = make_uint4(o[12], o[13], o[14], o[15]);
     }
   }
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     fence_gpu();
     unsigned int old = atomicAdd(&a.arrived[a.n_chunks], 1u);
     if (old + 1 == gridDim.x) {
+      fence_gpu();
       a.out[1] = t_start;
       a.out[2] = globaltimer_ns();
-      a.out[3] = a.arrived[a.n_chunks + 1];
-      for (uint32_t c = 0; c <= a.n_chunks + 1; ++c) a.arrived[c] = 0;   // self-clean
+      a.out[3] = *(volatile unsigned int*)&a.arrived[a.n_chunks + 1];
+      for (uint32_t c = 0; c <= a.n_chunks + 2; ++c) a.arrived[c] = 0;   // self-clean
     }
   }
 }
@@ -322,6 +342,7 @@ RN_API int rn_k_unpack_fp8(uint64_t stream, int grid, uint64_t staging, uint64_t
   uint32_t tiles_per_chunk = chunk_elems / kTileElems;
   if (grid <= 0) grid = 148;
   if ((uint32_t)grid > tiles_per_chunk) grid = (int)tiles_per_chunk;
+  if (qp_dev) grid += 1;                                      // CTA 0 polls the receive CQ, the others unpack
   unpack_fp8_kernel<<<grid, kPackThreads, 0, (cudaStream_t)stream>>>(a);
   return (int)cudaGetLastError();
 }

@@ -102,7 +102,7 @@ def unpack_fp8(ctx, staging: torch.Tensor, dst: torch.Tensor, chunk_elems: int =
     lib = N.load()
     ws = work_stream(ctx, stream)
     n_chunks = n // chunk_elems
-    arrived = ctx.dev_scratch((n_chunks + 2) * 4, offset=scratch_slot * (256 << 10))
+    arrived = ctx.dev_scratch((n_chunks + 3) * 4, offset=scratch_slot * (256 << 10))
     out_addr, out_view = ctx.scratch(64, offset=4096 + scratch_slot * 64)
     rc = lib.rn_k_unpack_fp8(_stream_ptr(ws), grid, staging.data_ptr(), dst.data_ptr(), n, chunk_elems,
                              qp.dev_ptr if qp is not None else 0, arrived, out_addr, timeout_ms)
