@@ -98,6 +98,8 @@ def unpack_fp8(ctx, staging: torch.Tensor, dst: torch.Tensor, chunk_elems: int =
     """fp8 chunk records -> bf16.  With ``qp`` the kernel waits for each record's receive
     CQE (RDMA_WRITE_IMM, immediate = chunk id) before touching it."""
     assert dst.dtype == torch.bfloat16 and dst.is_contiguous()
+    if (staging.data_ptr() | dst.data_ptr()) & 31:
+        raise ValueError("unpack_fp8: records and output must be 32-byte aligned (256-bit loads / stores)")
     n = dst.numel()
     lib = N.load()
     ws = work_stream(ctx, stream)
