@@ -68,7 +68,7 @@ def main():
     ap.add_argument("--msg-bytes", type=int, default=256 << 20)
     ap.add_argument("--engine-ctas", type=int, default=32)
     ap.add_argument("--window", type=int, default=8, help="work requests in flight per poster")
-    ap.add_argument("--min-seconds", type=float, default=1.2, help="lower bound on the timed region (msgs_per_step is sized for it)")
+    ap.add_argument("--min-seconds", type=float, default=2.0, help="lower bound on the timed region (msgs_per_step is sized for it)")
     ap.add_argument("--msgs-per-step", type=int, default=0, help="0 = calibrate")
     ap.add_argument("--extras", type=int, default=1, help="also run baselines' siblings: ring, fused pack, small messages, GEMM, mock NIC")
     args = ap.parse_args()
