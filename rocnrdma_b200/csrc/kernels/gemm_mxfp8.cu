@@ -10,7 +10,10 @@
 // operands, and (nominally) twice the tensor rate.  Round 1 had an fp8 EPILOGUE only; its records could be produced
 // but never consumed by a GEMM.
 //
-// One CTA per SM, persistent, 320 threads:
+// Two kernels.  gemm_mxfp8_pair_kernel (further down; the default for M > 128): a CTA pair per 256 x 256 tile, scale factors
+// written into TMEM by the loader warps, TMA-store epilogue, optional per-panel arrival words (receive-side fusion).
+// gemm_mxfp8_kernel (first; small M, and the reference the pair kernel is tested against): one CTA per 128 x 128 tile,
+// persistent, 320 threads:
 //   warp 0      TMA producer: 3-D tensor maps (K, rows-in-record, record) so an operand may live inside records;
 //               128 x 128-byte boxes, SWIZZLE_128B, out-of-bounds rows / K filled with zeros (ragged shapes)
 //   warp 1      MMA issuer: per 128-deep k-block two tcgen05.cp 32x128b.warpx4 copy the block's scale factors from
