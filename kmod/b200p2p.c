@@ -58,6 +58,9 @@ MODULE_SOFTDEP("pre: nvidia ib_core");
  *               1: also print them at INFO level -- for boxes whose kernel lacks CONFIG_DYNAMIC_DEBUG
  *   max_pin_mb  refuse to claim a range larger than this many MiB (0 = no limit): a guard rail for
  *               shared machines, acquire() then answers "not mine" and ibv_reg_mr() fails cleanly
+ *   enable      0: stay registered with ib_core but claim nothing new (existing registrations keep working and are torn
+ *               down normally) -- hands new registrations to another peer-memory client (stock nvidia-peermem) or
+ *               switches GPU registration off without unloading; the nvidia-peermem "peerdirect_support"-style switch
  */
 static int debug;
 module_param(debug, int, 0644);
@@ -65,6 +68,9 @@ MODULE_PARM_DESC(debug, "1: print per-callback breadcrumbs at INFO level");
 static unsigned long max_pin_mb;
 module_param(max_pin_mb, ulong, 0644);
 MODULE_PARM_DESC(max_pin_mb, "largest range (MiB) this client will claim, 0 = unlimited");
+static int enable = 1;
+module_param(enable, int, 0644);
+MODULE_PARM_DESC(enable, "0: claim no new ranges (existing registrations are unaffected)");
 
 #define MSG_DBG(fmt, args...)                                                       \
 	do {                                                                        \
@@ -291,6 +297,10 @@ static int b200_acquire(unsigned long addr, size_t size, void *peer_mem_private_
 
 	if (!size || !client_context)
 		return 0;
+	if (!enable) {
+		MSG_DBG("acquire: disabled (enable=0), not claiming 0x%lx\n", addr);
+		return 0;
+	}
 	pin_va = (u64)addr & GPU_PAGE_MASK;
 	pin_size = (((u64)addr + size + GPU_PAGE_SIZE - 1) & GPU_PAGE_MASK) - pin_va;
 	if (max_pin_mb && (pin_size >> 20) > max_pin_mb) {
@@ -657,8 +667,8 @@ DEFINE_SHOW_ATTRIBUTE(b200_stats);
 
 static int __init b200p2p_init(void)
 {
-	MSG_INFO("init (GPU page %llu KiB, debug=%d, max_pin_mb=%lu)\n", (unsigned long long)(GPU_PAGE_SIZE >> 10), debug,
-		 max_pin_mb);
+	MSG_INFO("init (GPU page %llu KiB, debug=%d, max_pin_mb=%lu, enable=%d)\n", (unsigned long long)(GPU_PAGE_SIZE >> 10), debug,
+		 max_pin_mb, enable);
 	atomic64_set(&stat_acquired, 0);
 	atomic64_set(&stat_pinned, 0);
 	atomic64_set(&stat_mapped, 0);

@@ -30,6 +30,7 @@ def lib():
         ("sim_live_allocs", C.c_long, []), ("sim_ib_client_name", C.c_char_p, []), ("sim_ib_client_version", C.c_char_p, []),
         ("sim_dev_name", C.c_char_p, []), ("sim_debugfs_read", C.c_int, [C.c_char_p, C.c_char_p, C.c_int]),
         ("sim_param_b200p2p_debug", None, [C.c_long]), ("sim_param_b200p2p_max_pin_mb", None, [C.c_long]),
+        ("sim_param_b200p2p_enable", None, [C.c_long]),
         ("sim_nv_revoke_during_dma_map", None, [u64]), ("sim_ib_set_release_in_invalidate", None, [C.c_int]),
     ]:
         getattr(l, name).restype, getattr(l, name).argtypes = res, args
@@ -307,6 +308,28 @@ def test_counters_are_browsable_in_debugfs_while_loaded(bridge):
     bridge.sim_ib_dereg_mr(b)
     st = _stats(bridge)
     assert st["revoked"] == 2 and st["released"] == 2 and st["live"] == 0
+
+
+def test_enable_parameter_stops_new_claims_and_leaves_live_registrations_alone(bridge):
+    """enable=0: the client stays registered but claims nothing new; what is registered keeps translating, is revoked by the
+    driver and is released as usual.  Back to 1: claims resume."""
+    bridge.sim_gpu_alloc(VA, 8 * PAGE)
+    live = bridge.sim_ib_reg_mr(VA, 2 * PAGE, 0)
+    assert live >= 0
+    bridge.sim_param_b200p2p_enable(0)
+    try:
+        assert bridge.sim_ib_reg_mr(VA + 4 * PAGE, PAGE, 0) == -95       # nobody claims the range: ibv_reg_mr fails cleanly
+        assert bridge.sim_live_pins() == 1                              # the probe pin never happened
+        bridge.sim_gpu_free(VA)                                         # the live registration is still revoked by the driver ...
+        assert _stats(bridge)["revoked"] == 1
+        bridge.sim_ib_dereg_mr(live)                                    # ... and released normally
+        assert _stats(bridge)["live"] == 0 and bridge.sim_live_pins() == 0
+    finally:
+        bridge.sim_param_b200p2p_enable(1)
+    bridge.sim_gpu_alloc(VA, 8 * PAGE)
+    mr = bridge.sim_ib_reg_mr(VA, PAGE, 0)
+    assert mr >= 0
+    bridge.sim_ib_dereg_mr(mr)
 
 
 def test_module_parameters(bridge):
