@@ -35,10 +35,11 @@ class MxOperand:
     @staticmethod
     def from_panel_records(rec: torch.Tensor, rows: int, K: int) -> "MxOperand":
         """The output of ``ops.gemm_send(..., out_fp8=True)`` (or its copy on the receiving side): one record per 128-row
-        panel, ``[128 x K fp8][128 x K/32 scales]``."""
-        assert rec.dtype == torch.uint8 and rows % PANEL_ROWS == 0
+        panel, ``[128 x K fp8][128 x K/32 scales]``.  ``rows`` need not be a multiple of 128: the last record is whole (the
+        epilogue quantises zeros for the rows past the end) and the GEMM only uses its first ``rows % 128`` rows."""
+        assert rec.dtype == torch.uint8
         stride = PANEL_ROWS * K + PANEL_ROWS * (K // BLOCK)
-        assert rec.numel() >= (rows // PANEL_ROWS) * stride
+        assert rec.numel() >= -(-rows // PANEL_ROWS) * stride
         return MxOperand(rec.data_ptr(), rec.data_ptr() + PANEL_ROWS * K, rows, K, PANEL_ROWS, stride, keepalive=rec)
 
     @staticmethod

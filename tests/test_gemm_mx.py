@@ -146,3 +146,22 @@ def test_mxfp8_starts_tiles_as_their_panels_arrive(ctx):
     xq = rcv.reshape(panels, -1)[:, :128 * N1].reshape(M, N1)
     xs = rcv.reshape(panels, -1)[:, 128 * N1:].reshape(M, N1 // 32)
     _check(y, xq, xs, wq, ws, N1)
+
+
+def test_mxfp8_consumes_ragged_panel_records(ctx):
+    """K4 at a ragged M emits ceil(M / 128) whole records; K7 multiplies exactly the M rows that exist."""
+    M, K1, N1, N2 = 300, 200, 288, 136
+    p, q = _rand(M, K1, spread=False), _rand(N1, K1, spread=False)
+    w = _rand(N2, N1)
+    wq, ws = MX.quantize_mx(w)
+    panels = -(-M // 128)
+    rec = torch.zeros(panels * ops.panel_record_bytes(N1), dtype=torch.uint8, device="cuda")
+    assert ops.gemm_send(ctx, p, q, rec, out_fp8=True).ok
+    y = torch.zeros(M, N2, device="cuda", dtype=torch.bfloat16)
+    for cg in (1, 2):
+        y.zero_()
+        assert ops.gemm_mxfp8(ctx, MX.MxOperand.from_panel_records(rec, M, N1), MX.MxOperand.from_tensors(wq, ws), y, cta_group=cg).ok
+        r = rec.reshape(panels, -1)
+        xq = r[:, :128 * N1].reshape(panels * 128, N1)[:M].contiguous()
+        xs = r[:, 128 * N1:].reshape(panels * 128, N1 // 32)[:M].contiguous()
+        _check(y, xq, xs, wq, ws, N1)
